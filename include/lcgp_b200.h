@@ -1,0 +1,143 @@
+/* lcgp_b200 -- C-ABI of the B200 (sm_100a) implementation of LCGP's emulator-fitting hot path.
+ *
+ * The reference (mosesyhc/LCGP, pure Python on TensorFlow) has no FFI: the seam is cut where its
+ * Python loops over the latent components call dense TF linear algebra.  Each entry point below
+ * names the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every array argument is a DEVICE pointer to row-major contiguous IEEE fp64 unless its name
+ *     ends in _host; the caller (torch) owns every buffer including the workspace; the library
+ *     allocates nothing and keeps no state between calls
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns
+ *     without synchronising (the *_host variants synchronise the stream before returning)
+ *   - return value: 0 = ok; < 0 = invalid argument (LCGP_E_*); >= 1000 = 1000 + cudaError_t.
+ *     Numerical failure (non-positive pivot) is reported per latent through `info`
+ *     (LAPACK style: 1-based index of the first bad pivot, 0 = ok), never by the return value
+ *   - dense factors are stored padded: np = LCGP_NB * ceil(n / LCGP_NB)
+ */
+#ifndef LCGP_B200_H
+#define LCGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCGP_NB 128
+#define LCGP_MAX_D 64
+
+#define LCGP_E_ARG (-1)        /* null pointer / non-positive size */
+#define LCGP_E_DIM (-2)        /* d > LCGP_MAX_D or np not a multiple of LCGP_NB */
+#define LCGP_E_WORKSPACE (-3)  /* workspace too small */
+
+/* Constant data of one rank's share of an emulator (all device pointers).
+ * rep mode (lcgp.py:554-630):  X = x_unique_s, sr = sqrt(r), YR = ybar_s * r (or ybar * r),
+ *   w_j = sum_i r_i ybar_ji^2, t = ybar_std (or ones), scale = 1/n, sum_log_r = sum_i log r_i
+ * full mode (lcgp.py:635-666): X = x (standardised), sr = ones, YR = y, w_j = sum_i y_ji^2, t = ones,
+ *   scale = 1, sum_log_r = 0 */
+typedef struct lcgp_problem {
+    int32_t n;       /* unique training inputs */
+    int32_t d;       /* input dimension */
+    int32_t p;       /* output dimension */
+    int32_t q_loc;   /* latent components handled by this rank */
+    int32_t include_host_terms; /* 1: add the O(p) data-fit / noise / -p/2 sum log r terms (one rank only) */
+    int32_t reserved;
+    double scale;       /* objective multiplier: 1/n (rep) or 1 (full) */
+    double sum_log_r;
+    const double* X;    /* n x d */
+    const double* sr;   /* n */
+    const double* YR;   /* p x n */
+    const double* w;    /* p */
+    const double* t;    /* p */
+    const double* phi;  /* p x q_loc  (this rank's columns of the basis) */
+    const double* D;    /* q_loc      (diag_D of this rank's latents) */
+} lcgp_problem;
+
+/* Length (in doubles) of the `out` vector of lcgp_nll_grad:
+ *   [0]                      objective contribution of this rank (scaled)
+ *   [1 .. p]                 d/d lsigma2 (p-vector, before the diag_error_structure segment-sum)
+ *   [1+p .. ]                d/d lLmb (q_loc x d), d/d lLmb0 (q_loc), d/d lnugGPs (q_loc)   (constrained values)
+ *   then                     logdet A_k (q_loc), b_k^T S_k b_k (q_loc)                       (diagnostics) */
+size_t lcgp_out_len(int32_t p, int32_t d, int32_t q_loc);
+
+/* Bytes of workspace needed by lcgp_nll_grad / lcgp_predict for a problem of this size. */
+size_t lcgp_workspace_bytes(int32_t n, int32_t d, int32_t p, int32_t q_loc);
+/* Bytes of scratch needed by lcgp_predict for n0 test points. */
+size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
+
+/* Objective and analytic gradient of this rank's latents.
+ * Replaces the body of neglpost_rep (lcgp.py:554-630) / neglpost (lcgp.py:635-666) and the TF
+ * autodiff driven from fit() (lcgp.py:537-540).  Parameters are the CONSTRAINED values:
+ * lLmb (q_loc x d length-scales), lLmb0 (q_loc variances), lnugGPs (q_loc), lsigma2s expanded to
+ * the p-vector of get_param (lcgp.py:515-532).
+ * flags: bit0 = also compute the gradient (otherwise only out[0] and the diagnostics are valid).
+ * After the call the workspace holds L_k, L_k^{-T}, alpha_k (= CinvMs, lcgp.py:781) and m_k (= mks,
+ * lcgp.py:779) for lcgp_predict / lcgp_get_aux -- i.e. it also replaces
+ * _compute_aux_predictive_quantities_rep (lcgp.py:728-803) and compute_aux_predictive_quantities
+ * (lcgp.py:685-726).
+ * stage_events: NULL or 5 cudaEvent_t recorded at: start, after kernel-matrix build, after Cholesky,
+ * after triangular inverse, end. */
+int lcgp_nll_grad(const lcgp_problem* prob, const double* lLmb, const double* lLmb0, const double* lnugGPs,
+                  const double* lsigma2_p, void* workspace, size_t workspace_bytes, double* out,
+                  int32_t* info, int32_t flags, void* const* stage_events, void* stream);
+
+/* Same, with the parameters and results in HOST memory (pinned or pageable): copies the
+ * parameters to the device, runs lcgp_nll_grad, copies `out` and `info` back and synchronises
+ * the stream.  This is the call the Python LCGP.loss()/fit() path makes once per evaluation. */
+int lcgp_nll_grad_host(const lcgp_problem* prob, const double* lLmb_host, const double* lLmb0_host,
+                       const double* lnugGPs_host, const double* lsigma2_p_host, void* workspace,
+                       size_t workspace_bytes, double* out_host, int32_t* info_host, int32_t flags,
+                       void* const* stage_events, void* stream);
+
+/* Latent predictive mean and variance at n0 standardised test inputs, from the factor left in the
+ * workspace by the last lcgp_nll_grad with the same parameters.
+ * Replaces the k-loops of predict_rep (lcgp.py:883-897) and predict_full (lcgp.py:827-835).
+ * same_inputs = 1 reproduces the reference's nugget-on-equal-inputs behaviour (covmat.py:46-53). */
+int lcgp_predict(const lcgp_problem* prob, const double* lLmb, const double* lLmb0, const double* lnugGPs,
+                 void* workspace, size_t workspace_bytes, const double* x0s, int32_t n0, int32_t same_inputs,
+                 void* scratch, size_t scratch_bytes, double* ghat /* q_loc x n0 */, double* gvar /* q_loc x n0 */,
+                 void* stream);
+
+/* Copies alpha (CinvMs) and m (mks), each q_loc x n, out of the workspace. */
+int lcgp_get_aux(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
+                 void* stream);
+
+/* A^{-1} of latent k (n x n, dense, symmetric) rebuilt from the factor in the workspace; used to
+ * materialise the reference's Tks / Ths on request (lcgp.py:783-788, 709-715). */
+int lcgp_get_Ainv(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, int32_t k, double* Ainv,
+                  void* stream);
+
+/* Matern32(x1, x2, llmb, llmb0, lnug) of covmat.py:5-55 (diag_only=False branch): out is n1 x n2.
+ * same_inputs: the caller's evaluation of `x1.shape == x2.shape and all(x1 == x2)` (covmat.py:46-49). */
+int lcgp_kernel_matrix(const double* x1, int32_t n1, const double* x2, int32_t n2, int32_t d, const double* llmb,
+                       const double* llmb0, const double* lnug, int32_t same_inputs, double* out, void* stream);
+
+/* ---- stage entry points (unit parity tests and the stage rooflines of bench.py) ---- */
+
+/* A_k = I + d_k (C_k o sqrt r sqrt r^T) (lcgp.py:616) for `batch` latents into padded np x np
+ * buffers F (lower triangle + diagonal; identity in the pad). */
+int lcgp_build_A(const double* X, const double* sr, int32_t n, int32_t d, const double* lLmb, const double* lLmb0,
+                 const double* lnugGPs, const double* D, int32_t batch, double* F, int32_t np, void* stream);
+
+/* In-place batched Cholesky of the lower triangles of `batch` padded np x np matrices
+ * (tf.linalg.cholesky, lcgp.py:617/775).  DL/DU receive the inverses of the NB x NB diagonal
+ * blocks and their transposes (batch x np/NB x NB x NB each); logdet_part (batch x np/NB, may be
+ * NULL) receives sum log L_ii per diagonal block. */
+int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
+                       int32_t* info, void* stream);
+
+/* Blocked triangular inverse: fills the strictly-upper NB-blocks of F with L^{-T}.
+ * scratch: lcgp_trtri_scratch_bytes(np, batch). */
+size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch);
+int lcgp_trtri_batched(double* F, int32_t np, int32_t batch, const double* DL, const double* DU, void* scratch,
+                       size_t scratch_bytes, void* stream);
+
+/* Library / build identification. */
+const char* lcgp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCGP_B200_H */

@@ -1,0 +1,412 @@
+// extern "C" surface of liblcgp_b200.so (see include/lcgp_b200.h) and the O(p n q) glue kernels
+// around the per-latent dense stages.
+#include "../../include/lcgp_b200.h"
+#include "gemm_dmma.cuh"
+#include "lcgp_internal.h"
+
+namespace lcgp {
+
+constexpr int JSPLIT = 8;  // split of the p-reduction in the B = V^T YR product
+
+// ---- workspace layout (doubles; every segment 32-double aligned) -------------------------------
+struct Workspace {
+    int n, d, p, q, np, nb, ntiles;
+    size_t fstride, dstride, tstride;
+    double *F, *DL, *DU, *T, *B, *alpha, *mk, *atil, *gemv_part, *logdet_part, *quad, *tile_part, *V, *Z, *bpart;
+    double *ell, *s0, *lnug, *lsig, *out;
+    int32_t* info;
+    size_t total_doubles;
+};
+
+static inline size_t al(size_t x) { return (x + 31) / 32 * 32; }
+
+static Workspace layout(int n, int d, int p, int q, void* basep) {
+    Workspace w;
+    w.n = n; w.d = d; w.p = p; w.q = q;
+    w.np = round_up(n, NB);
+    w.nb = w.np / NB;
+    w.ntiles = w.nb * (w.nb + 1) / 2;
+    w.fstride = (size_t)w.np * w.np;
+    w.dstride = (size_t)w.nb * NB * NB;
+    w.tstride = trtri_scratch_blocks(w.nb) * NB * NB;
+    double* base = (double*)basep;
+    size_t o = 0;
+    auto take = [&](size_t cnt) { double* ptr = base ? base + o : nullptr; o += al(cnt); return ptr; };
+    w.F = take((size_t)q * w.fstride);
+    w.DL = take((size_t)q * w.dstride);
+    w.DU = take((size_t)q * w.dstride);
+    w.T = take((size_t)q * w.tstride);
+    w.B = take((size_t)q * w.np);
+    w.alpha = take((size_t)q * w.np);
+    w.mk = take((size_t)q * w.np);
+    w.atil = take((size_t)q * w.np);
+    w.gemv_part = take((size_t)q * (w.nb + 1) * w.np);
+    w.logdet_part = take((size_t)q * w.nb);
+    w.quad = take((size_t)q);
+    w.tile_part = take((size_t)q * w.ntiles * (d + 2));
+    w.V = take((size_t)p * q);
+    w.Z = take((size_t)p * q);
+    w.bpart = take((size_t)JSPLIT * q * w.np);
+    w.ell = take((size_t)q * d);
+    w.s0 = take((size_t)q);
+    w.lnug = take((size_t)q);
+    w.lsig = take((size_t)p);
+    w.out = take(lcgp_out_len(p, d, q));
+    w.info = (int32_t*)take((size_t)(q + 1) / 2 + 1);
+    w.total_doubles = o;
+    return w;
+}
+
+static FactorView view_of(const Workspace& w) {
+    FactorView v;
+    v.F = w.F; v.DL = w.DL; v.DU = w.DU; v.np = w.np; v.nb = w.nb; v.fstride = w.fstride; v.dstride = w.dstride;
+    return v;
+}
+
+// ---- glue kernels -----------------------------------------------------------------------------
+// V[j][k] = s_j phi[j][k],  s_j = exp(-lsig_j / 2) t_j        (sigma_inv_sqrt * phi[:, k], lcgp.py:608)
+__global__ void prep_v_kernel(int p, int q, const double* __restrict__ lsig, const double* __restrict__ t,
+                              const double* __restrict__ phi, double* __restrict__ V) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p * q) return;
+    const int j = idx / q;
+    V[idx] = exp(-0.5 * lsig[j]) * t[j] * phi[idx];
+}
+
+// bpart[js][k][i] = sum_{j in slice js} V[j][k] YR[j][i]      (b_k = r * ybar^T v_k, lcgp.py:609-610)
+template <int KC>
+__global__ void __launch_bounds__(128)
+bmat_part_kernel(int n, int np, int p, int q, const double* __restrict__ V, const double* __restrict__ YR,
+                 double* __restrict__ bpart) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int js = blockIdx.y;
+    const int k0 = blockIdx.z * KC;
+    const int jper = (p + JSPLIT - 1) / JSPLIT;
+    const int j0 = js * jper, j1 = min(p, j0 + jper);
+    double acc[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c] = 0.0;
+    if (i < n) {
+        for (int j = j0; j < j1; ++j) {
+            const double yv = YR[(size_t)j * n + i];
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+                if (k0 + c < q) acc[c] += __ldg(V + (size_t)j * q + k0 + c) * yv;
+        }
+    }
+    if (i < np) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (k0 + c < q) bpart[((size_t)js * q + k0 + c) * np + i] = acc[c];
+    }
+}
+
+__global__ void bmat_reduce_kernel(int np, int q, const double* __restrict__ bpart, double* __restrict__ B) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)q * np) return;
+    double s = 0.0;
+#pragma unroll
+    for (int js = 0; js < JSPLIT; ++js) s += bpart[(size_t)js * q * np + idx];
+    B[idx] = s;
+}
+
+// Z[j][k] = sum_i YR[j][i] m_k[i]     (the only term coupling latents to the noise parameters)
+template <int KC>
+__global__ void __launch_bounds__(256)
+zmat_kernel(int n, int np, int p, int q, const double* __restrict__ YR, const double* __restrict__ mk,
+            double* __restrict__ Z) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    const int k0 = blockIdx.y * KC;
+    if (j >= p) return;
+    double acc[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c] = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double yv = YR[(size_t)j * n + i];
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (k0 + c < q) acc[c] += yv * mk[(size_t)(k0 + c) * np + i];
+    }
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        const double s = warp_sum(acc[c]);
+        if (lane == 0 && k0 + c < q) Z[(size_t)j * q + k0 + c] = s;
+    }
+}
+
+// Objective value, d/d lsigma2 and scaling of the kernel-parameter gradients.
+__global__ void __launch_bounds__(256)
+finalize_kernel(lcgp_problem P, int nb, int with_grad, const double* __restrict__ lsig,
+                const double* __restrict__ logdet_part, const double* __restrict__ quad,
+                const double* __restrict__ Z, double* __restrict__ out) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const int p = P.p, q = P.q_loc, d = P.d;
+    double* g_sig = out + 1;
+    double* g_kern = out + 1 + p;                       // q*d + q + q values
+    double* diag_logdet = g_kern + (size_t)q * d + 2 * q;
+    double* diag_quad = diag_logdet + q;
+    // latent part
+    double lat = 0.0;
+    for (int k = tid; k < q; k += 256) {
+        double ld = 0.0;
+        for (int b = 0; b < nb; ++b) ld += logdet_part[(size_t)k * nb + b];
+        diag_logdet[k] = 2.0 * ld;
+        diag_quad[k] = quad[k];
+        lat += ld - 0.5 * quad[k];
+    }
+    lat = block_sum(lat, red);
+    // host part: 1/2 sum_j s_j^2 w_j + n/2 sum_j (lsig_j - 2 log t_j) - p/2 sum log r   (lcgp.py:589-597, 663-664)
+    double host = 0.0;
+    for (int j = tid; j < p; j += 256) {
+        const double tj = P.t[j];
+        const double sj = exp(-0.5 * lsig[j]) * tj;
+        const double fit = 0.5 * sj * sj * P.w[j];
+        if (P.include_host_terms) host += fit + 0.5 * (double)P.n * (lsig[j] - 2.0 * log(tj));
+        if (with_grad) {
+            double zs = 0.0;
+            for (int k = 0; k < q; ++k) zs += P.phi[(size_t)j * q + k] * Z[(size_t)j * q + k];
+            double g = 0.5 * sj * zs;
+            if (P.include_host_terms) g += -fit + 0.5 * (double)P.n;
+            g_sig[j] = P.scale * g;
+        }
+    }
+    host = block_sum(host, red);
+    if (tid == 0) {
+        double tot = lat + host;
+        if (P.include_host_terms) tot -= 0.5 * (double)p * P.sum_log_r;
+        out[0] = P.scale * tot;
+    }
+    if (with_grad)
+        for (int c = tid; c < q * d + 2 * q; c += 256) g_kern[c] *= P.scale;
+}
+
+static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : 1000 + (int)e; }
+#define LCGP_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_rc(e__); } while (0)
+
+static int check_problem(const lcgp_problem* P) {
+    if (!P || P->n <= 0 || P->d <= 0 || P->p <= 0 || P->q_loc <= 0) return LCGP_E_ARG;
+    if (!P->X || !P->sr || !P->YR || !P->w || !P->t || !P->phi || !P->D) return LCGP_E_ARG;
+    if (P->d > LCGP_MAX_D) return LCGP_E_DIM;
+    return 0;
+}
+
+static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double* s0, const double* lnug,
+                         const double* lsig, const Workspace& w, double* out, int32_t* info, int flags,
+                         void* const* ev, cudaStream_t st) {
+    const int n = P->n, d = P->d, p = P->p, q = P->q_loc;
+    const int with_grad = flags & 1;
+    FactorView v = view_of(w);
+    KernelParams kp{ell, s0, lnug, P->D};
+    auto rec = [&](int i) { if (ev && ev[i]) cudaEventRecord((cudaEvent_t)ev[i], st); };
+    rec(0);
+    LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * q, st));
+    // b_k
+    prep_v_kernel<<<(p * q + 255) / 256, 256, 0, st>>>(p, q, lsig, P->t, P->phi, w.V);
+    LCGP_CUDA(cudaGetLastError());
+    bmat_part_kernel<8><<<dim3(w.np / 128, JSPLIT, (q + 7) / 8), 128, 0, st>>>(n, w.np, p, q, w.V, P->YR, w.bpart);
+    LCGP_CUDA(cudaGetLastError());
+    bmat_reduce_kernel<<<(unsigned)(((size_t)q * w.np + 255) / 256), 256, 0, st>>>(w.np, q, w.bpart, w.B);
+    LCGP_CUDA(cudaGetLastError());
+    // A_k
+    LCGP_CUDA(launch_build_A(P->X, P->sr, n, d, w.np, kp, w.F, w.fstride, q, st));
+    rec(1);
+    LCGP_CUDA(potrf_batched(v, w.DL, w.DU, q, w.logdet_part, info, st));
+    rec(2);
+    LCGP_CUDA(trtri_batched(v, w.T, w.tstride, q, st));
+    rec(3);
+    SolveArgs a;
+    a.n = n; a.d = d; a.p = p; a.np = w.np; a.nb = w.nb; a.q_loc = q;
+    a.X = P->X; a.sr = P->sr; a.B = w.B; a.kp = kp;
+    a.alpha = w.alpha; a.mk = w.mk; a.atil = w.atil; a.gemv_part = w.gemv_part; a.quad = w.quad;
+    LCGP_CUDA(solve_alpha(v, a, st));
+    double* g_kern = out + 1 + p;
+    if (with_grad) {
+        LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, g_kern + (size_t)q * d, g_kern + (size_t)q * d + q, st));
+        zmat_kernel<8><<<dim3((p + 7) / 8, (q + 7) / 8), 256, 0, st>>>(n, w.np, p, q, P->YR, w.mk, w.Z);
+        LCGP_CUDA(cudaGetLastError());
+    }
+    finalize_kernel<<<1, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
+    LCGP_CUDA(cudaGetLastError());
+    rec(4);
+    return 0;
+}
+
+}  // namespace lcgp
+
+using namespace lcgp;
+
+extern "C" {
+
+const char* lcgp_version(void) { return "lcgp_b200 0.1 (sm_100a; DMMA m8n8k4 GEMM, NB=128)"; }
+
+size_t lcgp_out_len(int32_t p, int32_t d, int32_t q_loc) {
+    return (size_t)1 + p + (size_t)q_loc * d + 2 * (size_t)q_loc + 2 * (size_t)q_loc;
+}
+
+size_t lcgp_workspace_bytes(int32_t n, int32_t d, int32_t p, int32_t q_loc) {
+    if (n <= 0 || d <= 0 || p <= 0 || q_loc <= 0) return 0;
+    Workspace w = layout(n, d, p, q_loc, nullptr);
+    return w.total_doubles * sizeof(double);
+}
+
+size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0) {
+    if (n <= 0 || q_loc <= 0 || n0 <= 0) return 0;
+    const size_t np = round_up(n, NB), n0p = round_up(n0, NB), nb = np / NB;
+    return sizeof(double) * (size_t)q_loc * (n0p * np + nb * n0p);
+}
+
+int lcgp_nll_grad(const lcgp_problem* P, const double* lLmb, const double* lLmb0, const double* lnugGPs,
+                  const double* lsigma2_p, void* workspace, size_t workspace_bytes, double* out, int32_t* info,
+                  int32_t flags, void* const* stage_events, void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!lLmb || !lLmb0 || !lnugGPs || !lsigma2_p || !workspace || !out || !info) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    return nll_grad_impl(P, lLmb, lLmb0, lnugGPs, lsigma2_p, w, out, info, flags, stage_events, (cudaStream_t)stream);
+}
+
+int lcgp_nll_grad_host(const lcgp_problem* P, const double* lLmb_h, const double* lLmb0_h, const double* lnug_h,
+                       const double* lsig_h, void* workspace, size_t workspace_bytes, double* out_h,
+                       int32_t* info_h, int32_t flags, void* const* stage_events, void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!lLmb_h || !lLmb0_h || !lnug_h || !lsig_h || !workspace || !out_h || !info_h) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int q = P->q_loc;
+    LCGP_CUDA(cudaMemcpyAsync(w.ell, lLmb_h, sizeof(double) * q * P->d, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.s0, lLmb0_h, sizeof(double) * q, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lnug, lnug_h, sizeof(double) * q, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lsig, lsig_h, sizeof(double) * P->p, cudaMemcpyHostToDevice, st));
+    rc = nll_grad_impl(P, w.ell, w.s0, w.lnug, w.lsig, w, w.out, w.info, flags, stage_events, st);
+    if (rc) return rc;
+    LCGP_CUDA(cudaMemcpyAsync(out_h, w.out, sizeof(double) * lcgp_out_len(P->p, P->d, q), cudaMemcpyDeviceToHost, st));
+    LCGP_CUDA(cudaMemcpyAsync(info_h, w.info, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
+    LCGP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int lcgp_predict(const lcgp_problem* P, const double* lLmb, const double* lLmb0, const double* lnugGPs,
+                 void* workspace, size_t workspace_bytes, const double* x0s, int32_t n0, int32_t same_inputs,
+                 void* scratch, size_t scratch_bytes, double* ghat, double* gvar, void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!lLmb || !lLmb0 || !lnugGPs || !workspace || !x0s || n0 <= 0 || !scratch || !ghat || !gvar) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    if (scratch_bytes < lcgp_predict_scratch_bytes(P->n, P->q_loc, n0)) return LCGP_E_WORKSPACE;
+    KernelParams kp{lLmb, lLmb0, lnugGPs, P->D};
+    return cuda_rc(predict_latents(view_of(w), P->n, P->d, P->X, P->sr, kp, w.atil, x0s, n0, same_inputs,
+                                   (double*)scratch, P->q_loc, ghat, gvar, (cudaStream_t)stream));
+}
+
+int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
+                 void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!workspace || !CinvMs || !mks) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rowb = sizeof(double) * P->n;
+    LCGP_CUDA(cudaMemcpy2DAsync(CinvMs, rowb, w.alpha, sizeof(double) * w.np, rowb, P->q_loc, cudaMemcpyDeviceToDevice, st));
+    LCGP_CUDA(cudaMemcpy2DAsync(mks, rowb, w.mk, sizeof(double) * w.np, rowb, P->q_loc, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- A^{-1} materialisation (diagnostic / Tks, Ths on request) -----------------------------------
+namespace lcgp {
+// Ainv[i][j] = sum_{k >= max(i,j)} U[i][k] U[j][k]; plain FP64 FMA kernel, 16x16 output tile per CTA.
+__global__ void __launch_bounds__(256)
+ainv_kernel(FactorView v, int kz, int n, double* __restrict__ Ainv) {
+    __shared__ double ui[16][17], uj[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+    const double* F = v.F + (size_t)kz * v.fstride;
+    const double* DU = v.DU + (size_t)kz * v.dstride;
+    auto U = [&](int i, int k) -> double {
+        if (k < i) return 0.0;
+        const int Ib = i / NB, Kb = k / NB;
+        if (Ib == Kb) return DU[(size_t)Ib * NB * NB + (size_t)(i % NB) * NB + (k % NB)];
+        return F[(size_t)i * v.np + k];
+    };
+    double acc = 0.0;
+    const int kstart = (max(i0, j0) / 16) * 16;
+    for (int k0 = kstart; k0 < v.np; k0 += 16) {
+        ui[ty][tx] = U(i0 + ty, k0 + tx);
+        uj[ty][tx] = U(j0 + ty, k0 + tx);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) acc += ui[ty][kk] * uj[tx][kk];
+        __syncthreads();
+    }
+    const int i = i0 + ty, j = j0 + tx;
+    if (i < n && j < n) Ainv[(size_t)i * n + j] = acc;
+}
+}  // namespace lcgp
+
+extern "C" {
+
+int lcgp_get_Ainv(const lcgp_problem* P, void* workspace, size_t workspace_bytes, int32_t k, double* Ainv, void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!workspace || !Ainv || k < 0 || k >= P->q_loc) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    const int g = (P->n + 15) / 16;
+    ainv_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(view_of(w), k, P->n, Ainv);
+    return cuda_rc(cudaGetLastError());
+}
+
+int lcgp_kernel_matrix(const double* x1, int32_t n1, const double* x2, int32_t n2, int32_t d, const double* llmb,
+                       const double* llmb0, const double* lnug, int32_t same_inputs, double* out, void* stream) {
+    if (!x1 || !x2 || !llmb || !llmb0 || !lnug || !out || n1 <= 0 || n2 <= 0 || d <= 0) return LCGP_E_ARG;
+    if (d > LCGP_MAX_D) return LCGP_E_DIM;
+    return cuda_rc(launch_matern_rect(x1, n1, x2, n2, d, llmb, llmb0, lnug, same_inputs, nullptr, out, n2, n1, n2, 1, 0,
+                                      (cudaStream_t)stream));
+}
+
+int lcgp_build_A(const double* X, const double* sr, int32_t n, int32_t d, const double* lLmb, const double* lLmb0,
+                 const double* lnugGPs, const double* D, int32_t batch, double* F, int32_t np, void* stream) {
+    if (!X || !sr || !lLmb || !lLmb0 || !lnugGPs || !D || !F || n <= 0 || d <= 0 || batch <= 0) return LCGP_E_ARG;
+    if (d > LCGP_MAX_D || np % NB != 0 || np < n) return LCGP_E_DIM;
+    KernelParams kp{lLmb, lLmb0, lnugGPs, D};
+    return cuda_rc(launch_build_A(X, sr, n, d, np, kp, F, (size_t)np * np, batch, (cudaStream_t)stream));
+}
+
+int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
+                       int32_t* info, void* stream) {
+    if (!F || !DL || !DU || !info || np <= 0 || batch <= 0) return LCGP_E_ARG;
+    if (np % NB != 0) return LCGP_E_DIM;
+    FactorView v;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
+    cudaStream_t st = (cudaStream_t)stream;
+    LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+    return cuda_rc(potrf_batched(v, DL, DU, batch, logdet_part, info, st));
+}
+
+size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch) {
+    if (np <= 0 || batch <= 0 || np % NB != 0) return 0;
+    return sizeof(double) * (size_t)batch * trtri_scratch_blocks(np / NB) * NB * NB;
+}
+
+int lcgp_trtri_batched(double* F, int32_t np, int32_t batch, const double* DL, const double* DU, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+    if (!F || !DL || !DU || np <= 0 || batch <= 0) return LCGP_E_ARG;
+    if (np % NB != 0) return LCGP_E_DIM;
+    const size_t need = lcgp_trtri_scratch_bytes(np, batch);
+    if (need > 0 && (!scratch || scratch_bytes < need)) return LCGP_E_WORKSPACE;
+    FactorView v;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
+    return cuda_rc(trtri_batched(v, (double*)scratch, trtri_scratch_blocks(v.nb) * NB * NB, batch, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Internal (C++) declarations shared between the translation units of liblcgp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace lcgp {
+
+struct FactorView;
+
+// potrf.cu
+cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
+                          int* info, cudaStream_t stream);
+size_t trtri_scratch_blocks(int nb);
+cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);
+
+// Per-latent kernel hyper-parameters, device arrays of length q_loc (ell: q_loc x d).
+struct KernelParams {
+    const double* ell;
+    const double* s0;
+    const double* lnug;
+    const double* D;  // diag_D of the local latents
+};
+
+// matern.cu
+cudaError_t launch_matern_rect(const double* x1, int n1, const double* x2, int n2, int d, const double* ell,
+                               const double* s0, const double* lnug, int same, const double* colscale,
+                               double* out, int ld_out, int rows_out, int cols_out, int batch,
+                               size_t out_stride, cudaStream_t stream);
+cudaError_t launch_build_A(const double* X, const double* sr, int n, int d, int np, KernelParams kp,
+                           double* F, size_t fstride, int batch, cudaStream_t stream);
+
+// solve_grad.cu
+struct SolveArgs {
+    int n, d, p, np, nb, q_loc;
+    const double* X;     // n x d
+    const double* sr;    // n
+    const double* B;     // q_loc x np   (b_k, zero padded)
+    KernelParams kp;
+    double* alpha;       // q_loc x np   out
+    double* mk;          // q_loc x np   out
+    double* atil;        // q_loc x np   out  (A^{-1}(b / sqrt r))
+    double* gemv_part;   // q_loc x nb x np scratch
+    double* quad;        // q_loc out: b^T m
+};
+cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream);
+cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part /* q_loc x ntiles x (d+2) */,
+                          double* g_ell, double* g_s0, double* g_lnug, cudaStream_t stream);
+
+// predict.cu
+cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,
+                            const double* atil, const double* x0s, int n0, int same, double* scratch,
+                            int q_loc, double* ghat, double* gvar, cudaStream_t stream);
+
+}  // namespace lcgp

@@ -1,0 +1,275 @@
+// Solves against the factor and the fused analytic-gradient contraction.
+//
+// With U = L^{-T} held in the upper triangle (see gemm_dmma.cuh) the per-latent quantities are
+//   atil  = A^{-1} (b / sqrt r) = U (U^T v)                       (two memory-bound triangular mat-vecs)
+//   alpha = sqrt(r) o atil      (= CinvM_k, lcgp.py:781)
+//   m     = (b - alpha) / (d_k r)   (= C_k alpha = S_k b_k = mks, lcgp.py:779, from A atil = v)
+//   quad  = b^T m
+// and the gradient of T_k = 1/2 logdet A_k - 1/2 b^T S_k b wrt the kernel hyper-parameters is
+//   dT/dtheta = 1/2 sum_ij G_ij dC_ij/dtheta,   G = d_k (sqrt r sqrt r^T) o A^{-1} - alpha alpha^T.
+// ContractJob produces every 128x128 tile of A^{-1} = U U^T on the FP64 tensor pipe and consumes
+// it in registers against dC/dtheta tiles recomputed from X in shared memory; neither A^{-1} nor
+// any dC/dtheta matrix is written to HBM.
+#include "gemm_dmma.cuh"
+#include "lcgp_internal.h"
+
+namespace lcgp {
+
+// ---- y = U^T v :  y[k] = sum_{i <= k} U[i][k] v[i] -----------------------------------------------
+__global__ void __launch_bounds__(NB)
+gemv_ut_part_kernel(FactorView v, const double* __restrict__ B, const double* __restrict__ sr, int n,
+                    double* __restrict__ part /* [batch][nb][np] */) {
+    const int Kb = blockIdx.x, Ib = blockIdx.y, bz = blockIdx.z;
+    if (Ib > Kb) return;
+    __shared__ double vs[NB];
+    const int c = threadIdx.x;
+    {
+        const int gi = Ib * NB + c;
+        vs[c] = gi < n ? B[(size_t)bz * v.np + gi] / sr[gi] : 0.0;
+    }
+    __syncthreads();
+    const double* tile;
+    size_t ld;
+    if (Ib == Kb) { tile = v.DU + (size_t)bz * v.dstride + (size_t)Ib * NB * NB; ld = NB; }
+    else { tile = v.F + (size_t)bz * v.fstride + (size_t)Ib * NB * v.np + (size_t)Kb * NB; ld = v.np; }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < NB; i += 4) {
+        s0 += tile[(size_t)(i + 0) * ld + c] * vs[i + 0];
+        s1 += tile[(size_t)(i + 1) * ld + c] * vs[i + 1];
+        s2 += tile[(size_t)(i + 2) * ld + c] * vs[i + 2];
+        s3 += tile[(size_t)(i + 3) * ld + c] * vs[i + 3];
+    }
+    part[((size_t)bz * v.nb + Ib) * v.np + (size_t)Kb * NB + c] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void gemv_ut_reduce_kernel(int np, int nb, const double* __restrict__ part, double* __restrict__ y) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bz = blockIdx.y;
+    if (k >= np) return;
+    const int Kb = k / NB;
+    double s = 0.0;
+    for (int Ib = 0; Ib <= Kb; ++Ib) s += part[((size_t)bz * nb + Ib) * np + k];
+    y[(size_t)bz * np + k] = s;
+}
+
+// ---- atil = U y (one warp per row), then alpha, m ----------------------------------------------
+__global__ void __launch_bounds__(256)
+gemv_u_kernel(FactorView v, const double* __restrict__ y, const double* __restrict__ B,
+              const double* __restrict__ sr, const double* __restrict__ Dk, int n,
+              double* __restrict__ atil, double* __restrict__ alpha, double* __restrict__ mk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    const int bz = blockIdx.y;
+    if (i >= v.np) return;
+    const int I = i / NB, il = i % NB;
+    const double* yk = y + (size_t)bz * v.np;
+    const double* durow = v.DU + (size_t)bz * v.dstride + (size_t)I * NB * NB + (size_t)il * NB;
+    double s = 0.0;
+    for (int c = lane; c < NB; c += 32) s += durow[c] * yk[I * NB + c];
+    const double* frow = v.F + (size_t)bz * v.fstride + (size_t)i * v.np;
+    for (int k = (I + 1) * NB + lane; k < v.np; k += 32) s += frow[k] * yk[k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        const size_t o = (size_t)bz * v.np + i;
+        if (i < n) {
+            const double r = sr[i];
+            const double al = r * s;
+            atil[o] = s;
+            alpha[o] = al;
+            mk[o] = (B[o] - al) / (Dk[bz] * (r * r));
+        } else {
+            atil[o] = 0.0;
+            alpha[o] = 0.0;
+            mk[o] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+quad_kernel(int np, const double* __restrict__ B, const double* __restrict__ mk, double* __restrict__ quad) {
+    __shared__ double red[8];
+    const int bz = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) s += B[(size_t)bz * np + i] * mk[(size_t)bz * np + i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) quad[bz] = s;
+}
+
+// gemv_part holds q_loc * nb * np partial sums followed by q_loc * np doubles for y = U^T v.
+cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream) {
+    gemv_ut_part_kernel<<<dim3(v.nb, v.nb, a.q_loc), NB, 0, stream>>>(v, a.B, a.sr, a.n, a.gemv_part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    double* ybuf = a.gemv_part + (size_t)a.q_loc * v.nb * v.np;
+    gemv_ut_reduce_kernel<<<dim3((v.np + 255) / 256, a.q_loc), 256, 0, stream>>>(v.np, v.nb, a.gemv_part, ybuf);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    gemv_u_kernel<<<dim3((v.np + 7) / 8, a.q_loc), 256, 0, stream>>>(v, ybuf, a.B, a.sr, a.kp.D, a.n, a.atil,
+                                                                      a.alpha, a.mk);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    quad_kernel<<<a.q_loc, 256, 0, stream>>>(v.np, a.B, a.mk, a.quad);
+    return cudaGetLastError();
+}
+
+// ---- fused A^{-1} tile + gradient contraction ---------------------------------------------------
+struct ContractParams {
+    FactorView v;
+    int n, d;
+    const double* X;
+    const double* sr;
+    const double* alpha;  // [batch][np]
+    KernelParams kp;
+    double* tile_part;    // [batch][ntiles][d + 2] : (s0, lnug, ell_0..ell_{d-1}), unscaled
+    int ntiles;
+};
+
+struct ContractJob {
+    static constexpr bool kBNMajor = false;
+    typedef ContractParams Params;
+    int kb0, kb1, I, J;
+    const double* base;
+    const double* du;
+    __device__ bool init(const Params& p) {
+        if ((int)blockIdx.x >= p.ntiles) return false;
+        tri_decode(blockIdx.x, I, J);
+        kb0 = I;
+        kb1 = p.v.nb;
+        base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
+        du = p.v.DU + (size_t)blockIdx.y * p.v.dstride;
+        return true;
+    }
+    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
+        if (kb == I) { ptr = du + (size_t)I * NB * NB; ld = NB; }
+        else { ptr = base + (size_t)I * NB * p.v.np + (size_t)kb * NB; ld = p.v.np; }
+    }
+    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
+        if (kb == J) { ptr = du + (size_t)J * NB * NB; ld = NB; }
+        else { ptr = base + (size_t)J * NB * p.v.np + (size_t)kb * NB; ld = p.v.np; }
+    }
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double* smem, const WarpCoord& wc) const {
+        const int d = p.d, n = p.n, k = blockIdx.y, tid = threadIdx.x;
+        double* xi = smem;                 // [d][NB]   x_i / ell
+        double* xj = xi + d * NB;          // [d][NB]
+        double* sri = xj + d * NB;         // sqrt r (0 in the pad)
+        double* srj = sri + NB;
+        double* ai = srj + NB;             // alpha
+        double* aj = ai + NB;
+        double* red = aj + NB;             // [(d + 2)][8]
+        const double* ell = p.kp.ell + (size_t)k * d;
+        for (int idx = tid; idx < NB * d; idx += GEMM_THREADS) {
+            const int m = idx / NB, r = idx % NB;
+            const int gi = I * NB + r, gj = J * NB + r;
+            const double l = ell[m];
+            xi[idx] = gi < n ? p.X[(size_t)gi * d + m] / l : 0.0;
+            xj[idx] = gj < n ? p.X[(size_t)gj * d + m] / l : 0.0;
+        }
+        if (tid < NB) {
+            const int gi = I * NB + tid, gj = J * NB + tid;
+            sri[tid] = gi < n ? p.sr[gi] : 0.0;
+            srj[tid] = gj < n ? p.sr[gj] : 0.0;
+            ai[tid] = p.alpha[(size_t)k * p.v.np + gi];
+            aj[tid] = p.alpha[(size_t)k * p.v.np + gj];
+        }
+        __syncthreads();
+        const double s0 = p.kp.s0[k], lnug = p.kp.lnug[k], dk = p.kp.D[k];
+        const double nu = lnug / (1.0 + lnug);
+        const int cbase = wc.wn * 32 + 2 * wc.t;  // + ni*8 + e
+        double acc_s0 = 0.0, acc_nug = 0.0;
+        // pass 1: C0 per element; acc <- G * C0
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+            const int r = wc.row(mi);
+            double P[8], V[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { P[e] = 1.0; V[e] = 0.0; }
+            for (int m = 0; m < d; ++m) {
+                const double a = xi[m * NB + r];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double2 b = *reinterpret_cast<const double2*>(xj + m * NB + cbase + ni * 8);
+                    const double S0 = fabs(a - b.x), S1 = fabs(a - b.y);
+                    P[2 * ni] *= (1.0 + S0);
+                    V[2 * ni] -= S0;
+                    P[2 * ni + 1] *= (1.0 + S1);
+                    V[2 * ni + 1] -= S1;
+                }
+            }
+            const double dsr = dk * sri[r], al = ai[r];
+            const int gi = I * NB + r;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = cbase + ni * 8 + e;
+                    const double c0 = P[2 * ni + e] * exp(V[2 * ni + e]);
+                    const double G = dsr * srj[c] * acc[mi][ni][e] - al * aj[c];
+                    const double delta = (gi == J * NB + c) ? 1.0 : 0.0;
+                    acc_s0 += G * ((1.0 - nu) * c0 + nu * delta);
+                    acc_nug += G * (delta - c0);
+                    acc[mi][ni][e] = G * c0;
+                }
+        }
+        const int warp = tid >> 5, lane = tid & 31;
+        acc_s0 = warp_sum(acc_s0);
+        acc_nug = warp_sum(acc_nug);
+        if (lane == 0) { red[0 * 8 + warp] = acc_s0; red[1 * 8 + warp] = acc_nug; }
+        // pass 2: sum_ij (G C0)_ij S_m^2 / (1 + S_m) per input dimension m
+        for (int m = 0; m < d; ++m) {
+            double a[8];
+            double2 b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = xi[m * NB + wc.row(mi)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double2*>(xj + m * NB + cbase + ni * 8);
+            double sum = 0.0;
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double S0 = fabs(a[mi] - b[ni].x), S1 = fabs(a[mi] - b[ni].y);
+                    sum += acc[mi][ni][0] * (S0 * S0 / (1.0 + S0));
+                    sum += acc[mi][ni][1] * (S1 * S1 / (1.0 + S1));
+                }
+            sum = warp_sum(sum);
+            if (lane == 0) red[(2 + m) * 8 + warp] = sum;
+        }
+        __syncthreads();
+        if (tid < d + 2) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[tid * 8 + w];
+            const double wt = (I == J) ? 0.5 : 1.0;  // 1/2 * (1 or 2 for the mirrored tile)
+            double val;
+            if (tid == 0) val = wt * s;
+            else if (tid == 1) val = wt * s0 * s / ((1.0 + lnug) * (1.0 + lnug));
+            else val = wt * s0 * (1.0 - nu) * s / ell[tid - 2];
+            p.tile_part[((size_t)k * p.ntiles + blockIdx.x) * (d + 2) + tid] = val;
+        }
+    }
+};
+
+__global__ void contract_reduce_kernel(int ntiles, int d, const double* __restrict__ tile_part,
+                                       double* __restrict__ g_ell, double* __restrict__ g_s0,
+                                       double* __restrict__ g_lnug) {
+    const int k = blockIdx.x, c = threadIdx.x;
+    if (c >= d + 2) return;
+    double s = 0.0;
+    for (int t = 0; t < ntiles; ++t) s += tile_part[((size_t)k * ntiles + t) * (d + 2) + c];
+    if (c == 0) g_s0[k] = s;
+    else if (c == 1) g_lnug[k] = s;
+    else g_ell[(size_t)k * d + (c - 2)] = s;
+}
+
+cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part, double* g_ell,
+                          double* g_s0, double* g_lnug, cudaStream_t stream) {
+    const int ntiles = v.nb * (v.nb + 1) / 2;
+    ContractParams p{v, a.n, a.d, a.X, a.sr, a.alpha, a.kp, tile_part, ntiles};
+    cudaError_t e = gemm_launch<ContractJob>(p, dim3(ntiles, a.q_loc, 1), stream);
+    if (e != cudaSuccess) return e;
+    contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
+    return cudaGetLastError();
+}
+
+}  // namespace lcgp

@@ -1,0 +1,826 @@
+"""`LCGP` -- drop-in for the reference's model object (src/lcgp/lcgp.py:19-930) with the
+emulator-fitting hot path on sm_100a CUDA kernels behind the C-ABI of include/lcgp_b200.h.
+
+What stays on the host (torch CPU, float64): input checking, standardisation, replicate grouping,
+the SVD basis, the parameter container with its soft-clip bijectors, and the L-BFGS outer loop.
+What runs on the GPU, once per objective evaluation: kernel-matrix build, batched Cholesky,
+triangular inverse, solves, log-determinants and the analytic gradient (one `lcgp_nll_grad_host`
+call), and -- for `predict` -- the cross-covariance products against the same factor.
+
+There is no CPU fallback: `loss()`, `fit()` and `predict()` raise without a CUDA device / built
+library.  With `torch.distributed` initialised (one process per GPU) the q independent latent GPs
+are sharded round-robin over the ranks and one small all-reduce per evaluation combines the
+objective and the gradient; every rank then holds identical values, so the
+replicated host optimizer stays in lock-step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .parameter import Parameter, SoftClip
+
+DT = torch.float64
+
+
+# --------------------------------------------------------------------------------------------
+# small host helpers
+# --------------------------------------------------------------------------------------------
+def _as_tensor2d(t):
+    """lcgp.py:248-258: cast to float64 tensor, at least 2-D (a 1-D input becomes a column)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t), dtype=DT)
+    t = t.detach().to('cpu', DT)
+    if t.ndim < 2:
+        t = t.unsqueeze(1)
+    return t
+
+
+def _nearest_rank_median(Y):
+    """50th percentile along axis 1 with 'nearest' interpolation (what tfp.stats.percentile does by
+    default, lcgp.py:317-318/388-389): element round((m-1)/2) (half to even) of the ascending sort."""
+    m = Y.shape[1]
+    k = int(np.round((m - 1) * 0.5))
+    return torch.kthvalue(Y, k + 1, dim=1, keepdim=True).values
+
+
+def _itensor(v):
+    return torch.tensor(int(v), dtype=torch.int32)
+
+
+class _NegLogPost(torch.autograd.Function):
+    """Objective of all latents as one autograd node: forward runs the CUDA path and keeps the
+    analytic gradient; backward scales it.  The soft-clip chain rule and the
+    diag_error_structure segment-sum are left to torch autograd on the host."""
+
+    @staticmethod
+    def forward(ctx, model, lLmb, lLmb0, lsig_p, lnug):
+        need_grad = any(ctx.needs_input_grad[1:])
+        val, grads = model._evaluate(lLmb.detach(), lLmb0.detach(), lsig_p.detach(), lnug.detach(), need_grad)
+        if need_grad:
+            ctx.save_for_backward(*grads)
+        return val
+
+    @staticmethod
+    def backward(ctx, gout):
+        g_lLmb, g_lLmb0, g_lsig, g_lnug = ctx.saved_tensors
+        return None, gout * g_lLmb, gout * g_lLmb0, gout * g_lsig, gout * g_lnug
+
+
+class CudaEngine:
+    """Device-resident constant data of this rank's latents + the C-ABI calls on them."""
+
+    def __init__(self, n, d, p, X, sr, YR, w, t, phi_loc, D_loc, scale, sum_log_r, include_host_terms, device=None):
+        _cabi.require_cuda()
+        self.lib = _cabi.lib()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.d, self.p = int(n), int(d), int(p)
+        self.q_loc = int(phi_loc.shape[1])
+        if self.d > _cabi.MAX_D:
+            raise ValueError(f'lcgp_b200 supports input dimension d <= {_cabi.MAX_D}')
+        dev = self.device
+        c = lambda a: a.to(dev, DT).contiguous()
+        self.X, self.sr, self.YR, self.w, self.t = c(X), c(sr), c(YR), c(w), c(t)
+        self.phi, self.D = c(phi_loc), c(D_loc)
+        self.prob = _cabi.Problem(n=self.n, d=self.d, p=self.p, q_loc=self.q_loc,
+                                  include_host_terms=int(bool(include_host_terms)), reserved=0,
+                                  scale=float(scale), sum_log_r=float(sum_log_r),
+                                  X=self.X.data_ptr(), sr=self.sr.data_ptr(), YR=self.YR.data_ptr(),
+                                  w=self.w.data_ptr(), t=self.t.data_ptr(), phi=self.phi.data_ptr(),
+                                  D=self.D.data_ptr())
+        self.ws_bytes = int(self.lib.lcgp_workspace_bytes(self.n, self.d, self.p, self.q_loc))
+        self.ws = torch.empty(self.ws_bytes // 8, dtype=DT, device=dev)
+        self.out_len = int(self.lib.lcgp_out_len(self.p, self.d, self.q_loc))
+        q, dd = self.q_loc, self.d
+        # pinned host staging: [lLmb | lLmb0 | lnug | lsig_p] and the result vector
+        self.h_par = torch.empty(q * dd + 2 * q + self.p, dtype=DT).pin_memory()
+        self.h_out = torch.empty(self.out_len, dtype=DT).pin_memory()
+        self.h_info = torch.zeros(max(q, 1), dtype=torch.int32).pin_memory()
+        self.d_par = torch.empty(q * dd + 2 * q + self.p, dtype=DT, device=dev)
+        self.d_out = torch.empty(self.out_len, dtype=DT, device=dev)
+        self.d_info = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
+        self.h2d_bytes = self.h_par.numel() * 8
+        self.d2h_bytes = self.out_len * 8 + q * 4
+        self.launches_per_eval = self._count_launches()
+        self._scratch = None
+
+    def _count_launches(self):
+        nb = _cabi.padded(self.n) // _cabi.NB
+        levels = 0
+        s = 1
+        while s < nb:
+            levels += 1
+            s *= 2
+        # prep(3) + build(1) + potrf(nb diag + (nb-1)*(trsm+syrk)) + trtri(2/level) + solve(4) + contract(2) + zmat + finalize
+        return 3 + 1 + nb + 2 * (nb - 1) + 2 * levels + 4 + 2 + 1 + 1
+
+    def _stage(self, lLmb, lLmb0, lnug, lsig_p):
+        q, dd = self.q_loc, self.d
+        h = self.h_par
+        h[:q * dd].copy_(lLmb.reshape(-1))
+        h[q * dd:q * dd + q].copy_(lLmb0.reshape(-1))
+        h[q * dd + q:q * dd + 2 * q].copy_(lnug.reshape(-1))
+        h[q * dd + 2 * q:].copy_(lsig_p.reshape(-1))
+        return q * dd, q * dd + q, q * dd + 2 * q
+
+    def _events_arg(self, events):
+        if events is None:
+            return None
+        import ctypes as C
+        arr = (C.c_void_p * 5)(*[int(e.cuda_event) for e in events])
+        return arr
+
+    def evaluate(self, lLmb, lLmb0, lnug, lsig_p, with_grad=True, events=None):
+        """Host parameters in -> `out` vector (CPU tensor, layout of lcgp_out_len) via one
+        lcgp_nll_grad_host call (H2D of the parameters, all kernels, D2H of the result, sync)."""
+        o1, o2, o3 = self._stage(lLmb, lLmb0, lnug, lsig_p)
+        base = self.h_par.data_ptr()
+        with torch.cuda.device(self.device):
+            rc = self.lib.lcgp_nll_grad_host(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
+                                             self.ws.data_ptr(), self.ws_bytes, self.h_out.data_ptr(),
+                                             self.h_info.data_ptr(), int(bool(with_grad)), self._events_arg(events),
+                                             _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_nll_grad_host')
+        self._check_info(self.h_info)
+        return self.h_out.clone()
+
+    def evaluate_device(self, lLmb, lLmb0, lnug, lsig_p, with_grad=True, events=None):
+        """Same, but the result stays on the device (multi-rank path: all-reduce follows on the
+        same stream).  No host synchronisation."""
+        o1, o2, o3 = self._stage(lLmb, lLmb0, lnug, lsig_p)
+        with torch.cuda.device(self.device):
+            self.d_par.copy_(self.h_par, non_blocking=True)
+            base = self.d_par.data_ptr()
+            rc = self.lib.lcgp_nll_grad(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
+                                        self.ws.data_ptr(), self.ws_bytes, self.d_out.data_ptr(),
+                                        self.d_info.data_ptr(), int(bool(with_grad)), self._events_arg(events),
+                                        _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_nll_grad')
+        return self.d_out
+
+    def _check_info(self, info):
+        bad = torch.nonzero(info[:self.q_loc])
+        if bad.numel():
+            k = int(bad[0])
+            raise RuntimeError(f'lcgp_b200: Cholesky failed for local latent {k} at pivot {int(info[k])} '
+                               f'(A_k = I + d_k R^1/2 C_k R^1/2 has eigenvalues >= 1, so this means NaN/inf inputs)')
+
+    def predict_latents(self, lLmb, lLmb0, lnug, x0s, same):
+        """ghat, gvar (q_loc x n0) on the device from the factor left by the last evaluate()."""
+        o1, o2, _ = self._stage(lLmb, lLmb0, lnug, torch.zeros(self.p, dtype=DT))
+        n0 = int(x0s.shape[0])
+        with torch.cuda.device(self.device):
+            self.d_par.copy_(self.h_par, non_blocking=True)
+            x0d = x0s.to(self.device, DT).contiguous()
+            need = int(self.lib.lcgp_predict_scratch_bytes(self.n, self.q_loc, n0))
+            if self._scratch is None or self._scratch.numel() * 8 < need:
+                self._scratch = torch.empty(need // 8, dtype=DT, device=self.device)
+            ghat = torch.empty((self.q_loc, n0), dtype=DT, device=self.device)
+            gvar = torch.empty((self.q_loc, n0), dtype=DT, device=self.device)
+            base = self.d_par.data_ptr()
+            rc = self.lib.lcgp_predict(self.prob, base, base + 8 * o1, base + 8 * o2, self.ws.data_ptr(), self.ws_bytes,
+                                       x0d.data_ptr(), n0, int(bool(same)), self._scratch.data_ptr(),
+                                       self._scratch.numel() * 8, ghat.data_ptr(), gvar.data_ptr(), _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_predict')
+        return ghat, gvar
+
+    def aux(self):
+        a = torch.empty((self.q_loc, self.n), dtype=DT, device=self.device)
+        m = torch.empty((self.q_loc, self.n), dtype=DT, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.lcgp_get_aux(self.prob, self.ws.data_ptr(), self.ws_bytes, a.data_ptr(), m.data_ptr(),
+                                       _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_get_aux')
+        return a, m
+
+    def ainv(self, k):
+        A = torch.empty((self.n, self.n), dtype=DT, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.lcgp_get_Ainv(self.prob, self.ws.data_ptr(), self.ws_bytes, int(k), A.data_ptr(),
+                                        _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_get_Ainv')
+        return A
+
+
+class LCGP:
+    """Latent Component Gaussian Process.
+
+    submethod='full' uses all observations (x, y); submethod='rep' groups replicated x rows and
+    works on (x_unique, ybar).  Constructor arguments, attributes, methods and raised exception
+    types follow lcgp.py:31-41 and the reference test-suite; tensors are torch.float64.
+    Extra keyword arguments (not in the reference): `device`, `engine_factory` (tests only),
+    `shard` (shard latents over torch.distributed ranks when a process group is initialised).
+    """
+
+    def __init__(self, y=None, x=None, q: int = None, var_threshold: float = None,
+                 diag_error_structure: list = None, parameter_clamp_flag: bool = False,
+                 robust_mean: bool = True, submethod: str = 'full', rep_standardize_ybar: bool = True,
+                 verbose: bool = False, device=None, shard: bool = True, engine_factory=None):
+        self.verbose = verbose
+        self.robust_mean = robust_mean
+        self.rep_standardize_ybar = rep_standardize_ybar
+        self.parameter_clamp_flag = parameter_clamp_flag
+        self._device = device
+        self._engine_factory = engine_factory
+        self._engine = None
+
+        self.x = _as_tensor2d(x)
+        self.y = _as_tensor2d(y)
+
+        self.method = 'LCGP'
+        if submethod not in ['full', 'rep']:
+            raise ValueError('Invalid submethod. Choices are \'full\' or \'rep\'.')
+        self.submethod = submethod
+        self.submethod_loss_map = {'full': self.neglpost, 'rep': self.neglpost_rep}
+        self.submethod_predict_map = {'full': self.predict_full, 'rep': self.predict_rep}
+
+        if (q is not None) and (var_threshold is not None):
+            raise ValueError('Include only q or var_threshold but not both.')
+        self.q = q
+        self.var_threshold = var_threshold
+
+        self.n, self.d, self.p = self.verify_dim(self.y, self.x)
+        self.x_orig = self.x
+        self.y_orig = self.y
+
+        self.x, self.x_min, self.x_max, _ = self._standardize_x(self.x)
+        self._xnorm = None
+        self._rep_initialized = False
+
+        if self.submethod == 'rep':
+            (self.x_unique, self.x_unique_s, self.group_ids, self.r, _R, self.ybar, self.ybar_s,
+             self.ybar_mean, self.ybar_std, self.n, self.d, self.p) = self.preprocess()
+            self._rep_initialized = True
+        else:
+            self.y, self.ymean, self.ystd, _ = self.init_standard_y(self.y)
+
+        self.g, self.phi, self.diag_D, self.q = self.init_phi(var_threshold=var_threshold)
+
+        if diag_error_structure is None:
+            self.diag_error_structure = [1] * int(self.p)
+        else:
+            self.diag_error_structure = diag_error_structure
+        self.verify_error_structure(self.diag_error_structure, self.y)
+
+        d = int(self.d)
+        self.lLmb = Parameter(np.ones((self.q, d)), SoftClip(1e-6, 1e4), name='Latent GP log-scale')
+        self.lLmb0 = Parameter(np.ones(self.q), SoftClip(1e-4, 1e4), name='Latent GP log-lengthscale')
+        self.lsigma2s = Parameter(np.ones(len(self.diag_error_structure)), None, name='Diagonal error log-variance')
+        self.lnugGPs = Parameter(np.ones(self.q) * 1e-6, SoftClip(math.exp(-16.0), math.exp(-2.0)),
+                                 name='Latent GP nugget scale')
+        self.init_params()
+
+        # sharding of the latents over ranks
+        self._world, self._rank = 1, 0
+        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._world = torch.distributed.get_world_size()
+            self._rank = torch.distributed.get_rank()
+        self._local_idx = torch.arange(self._rank, self.q, self._world)
+
+        self._invalidate_aux()
+        self.ghat = None
+        self.gvar = None
+        self.psi_c = None
+        self.n_evals = 0
+
+    # ------------------------------------------------------------------ display
+    def __repr__(self):
+        rows = '\n'.join(f'\t\t{prm.name}\t{tuple(prm.shape)}\t{np.array2string(prm.numpy(), precision=4, threshold=8)}'
+                         for prm in (self.lLmb, self.lLmb0, self.lsigma2s, self.lnugGPs))
+        return ('LCGP(\n\tsubmethod:\t{:s}\n\toutput dimension:\t{:d}\n\tnumber of latent components:\t{:d}\n'
+                '\tparameter_clamping:\t{:s}\n\trobust_standardization:\t{:s}\n'
+                '\tdiagonal_error structure:\t{:s}\n\tparameters:\t\n{}\n)').format(
+                    self.submethod, int(self.p), int(self.q), str(self.parameter_clamp_flag),
+                    str(self.robust_mean), str(self.diag_error_structure), rows)
+
+    # ------------------------------------------------------------------ checks / transforms
+    @staticmethod
+    def _verify_data_types(t):
+        return _as_tensor2d(t)
+
+    def verify_dim(self, y, x):
+        """lcgp.py:260-270."""
+        p, ny = y.shape[0], y.shape[1]
+        nx, d = x.shape[0], x.shape[1]
+        assert ny == nx, 'Number of inputs (x) differs from number of outputs (y), y.shape[1] != x.shape[0]'
+        return _itensor(nx), _itensor(d), _itensor(p)
+
+    @staticmethod
+    def verify_error_structure(diag_error_structure, y):
+        """lcgp.py:272-278."""
+        assert sum(diag_error_structure) == y.shape[0], \
+            'Sum of error_structure should equal the output dimension.'
+
+    def tx_x(self, xs):
+        return xs * (self.x_max - self.x_min) + self.x_min
+
+    def tx_y(self, ys):
+        return ys * self.ystd + self.ymean
+
+    # ------------------------------------------------------------------ standardisation
+    @staticmethod
+    def _standardize_x(x):
+        x_max = x.max(dim=0).values
+        x_min = x.min(dim=0).values
+        return (x - x_min) / (x_max - x_min), x_min, x_max, x
+
+    @staticmethod
+    def _mean_positive_distance(x):
+        """Per input dimension: mean of |x_i - x_j| over ordered pairs with a positive distance
+        (what lcgp.py:304-309 computes from d dense N x N matrices), in O(N log N) from the sort:
+        sum_{i<j} (v_(j) - v_(i)) = sum_i v_(i) (2 i - N + 1)."""
+        N = x.shape[0]
+        out = torch.zeros(x.shape[1], dtype=DT)
+        for j in range(x.shape[1]):
+            v, _ = torch.sort(x[:, j])
+            total = 2.0 * (v * (2.0 * torch.arange(N, dtype=DT) - (N - 1))).sum()
+            _, counts = torch.unique_consecutive(v, return_counts=True)
+            pairs = float(N) * N - float((counts.to(DT) ** 2).sum())
+            out[j] = total / pairs if pairs > 0 else float('nan')
+        return out
+
+    @staticmethod
+    def init_standard_x(x):
+        """lcgp.py:295-310: (xs, x_min, x_max, x, xnorm)."""
+        xs, x_min, x_max, x = LCGP._standardize_x(x)
+        return xs, x_min, x_max, x, LCGP._mean_positive_distance(x)
+
+    @property
+    def xnorm(self):
+        # unused by the model (SURVEY B-7); computed on first access
+        if self._xnorm is None:
+            self._xnorm = self._mean_positive_distance(self.x_orig)
+        return self._xnorm
+
+    def _center_spread(self, Y, guard):
+        if self.robust_mean:
+            c = _nearest_rank_median(Y)
+            s = _nearest_rank_median(torch.abs(Y - c))
+        else:
+            c = Y.mean(dim=1, keepdim=True)
+            s = Y.std(dim=1, keepdim=True, unbiased=False)
+        if guard:   # lcgp.py:394 (rep path only)
+            s = torch.where(s > 0, s, torch.ones_like(s))
+        return c, s
+
+    def init_standard_y(self, y):
+        """lcgp.py:312-324."""
+        c, s = self._center_spread(y, guard=False)
+        return (y - c) / s, c, s, y
+
+    def _compute_center_spread_tf(self, Y):
+        """lcgp.py:383-395 (name kept for drop-in use)."""
+        return self._center_spread(torch.as_tensor(Y, dtype=DT), guard=True)
+
+    # ------------------------------------------------------------------ replication
+    def _get_raw_xy(self, x_raw=None, y_raw=None):
+        xr = self.x_orig if x_raw is None else x_raw
+        yr = self.y_orig if y_raw is None else y_raw
+        xr = xr.numpy() if isinstance(xr, torch.Tensor) else np.asarray(xr, dtype=np.float64)
+        yr = yr.numpy() if isinstance(yr, torch.Tensor) else np.asarray(yr, dtype=np.float64)
+        assert xr.ndim == 2, 'x_raw must be (N, d)'
+        assert yr.ndim == 2, 'y_raw must be (p, N)'
+        assert yr.shape[1] == xr.shape[0], 'y_raw columns must match x_raw rows'
+        return xr, yr, xr.shape[0], xr.shape[1], yr.shape[0]
+
+    @staticmethod
+    def _group_unique_rows_np(xr):
+        """lcgp.py:349-356: lexicographically sorted unique rows, inverse map, counts."""
+        xu, inv, cnt = np.unique(xr, axis=0, return_inverse=True, return_counts=True)
+        return xu, np.asarray(inv).reshape(-1), cnt
+
+    @staticmethod
+    def _compute_ybar_np(yr, inverse, n):
+        """Replicate means on the raw scale (lcgp.py:358-367) as one segment-sum."""
+        p = yr.shape[0]
+        sums = np.zeros((p, n), dtype=np.float64)
+        np.add.at(sums.T, inverse, yr.T)
+        return sums / np.bincount(inverse, minlength=n)[None, :]
+
+    def preprocess(self, y_raw=None, x_raw=None):
+        """lcgp.py:397-426: 12-tuple of replication structures."""
+        xr, yr, N, d, p = self._get_raw_xy(x_raw=x_raw, y_raw=y_raw)
+        xu, inv, cnt = self._group_unique_rows_np(xr)
+        n_unique = int(xu.shape[0])
+        ybar = torch.as_tensor(self._compute_ybar_np(yr, inv, n_unique), dtype=DT)
+        x_unique = torch.as_tensor(xu, dtype=DT)
+        x_unique_s = (x_unique - self.x_min) / (self.x_max - self.x_min)
+        group_ids = torch.as_tensor(inv, dtype=torch.int32)
+        r = torch.as_tensor(cnt.astype(np.int32))
+        R = _LazyDiag(r)
+        ybar_mean, ybar_std = self._compute_center_spread_tf(ybar)
+        ybar_s = (ybar - ybar_mean) / ybar_std
+        return (x_unique, x_unique_s, group_ids, r, R, ybar, ybar_s, ybar_mean, ybar_std,
+                _itensor(n_unique), _itensor(d), _itensor(p))
+
+    @property
+    def R(self):
+        return torch.diag(self.r.to(DT))
+
+    def _ensure_replication(self):
+        if not self._rep_initialized:
+            self.preprocess()
+            self._rep_initialized = True
+
+    # ------------------------------------------------------------------ basis
+    def _get_phi_input(self):
+        """lcgp.py:439-452."""
+        if self.submethod != 'rep':
+            return self.y
+        if getattr(self, 'rep_standardize_ybar', True) and hasattr(self, 'ybar_s'):
+            return self.ybar_s
+        if hasattr(self, 'ybar'):
+            return self.ybar
+        return self.y
+
+    def init_phi(self, var_threshold: float = None):
+        """lcgp.py:454-485: phi = U_q sqrt(n) / s_q from the SVD of the (standardised) outputs."""
+        Y = self._get_phi_input()
+        n, p = int(self.n), int(self.p)
+        U, s, _ = torch.linalg.svd(Y, full_matrices=False)
+        if (self.q is None) and (var_threshold is None):
+            q = p
+        elif (self.q is None) and (var_threshold is not None):
+            cum = np.cumsum(s.numpy() ** 2) / np.sum(s.numpy() ** 2)
+            q = int(np.argmax(cum > var_threshold) + 1) if np.any(cum > var_threshold) else p
+        else:
+            q = int(self.q)
+        assert U.shape[1] == min(n, p)
+        phi = U[:, :q] * math.sqrt(n) / s[:q]
+        diag_D = (phi ** 2).sum(dim=0)
+        g = phi.T @ Y
+        if self.verbose:   # the reference prints unconditionally (lcgp.py:482-483)
+            print('======= VARIANCE OF G ======')
+            print(g.var(dim=1, unbiased=False))
+        return g, phi, diag_D, q
+
+    # ------------------------------------------------------------------ parameters
+    def init_params(self):
+        """lcgp.py:490-513."""
+        x = self.x.numpy()
+        d = int(self.d)
+        llmb = np.exp(0.5 * np.log(d) + np.log(np.std(x, axis=0)))
+        ynp = self.y.numpy()
+        lsig = np.zeros(len(self.diag_error_structure))
+        col = 0
+        for k, width in enumerate(self.diag_error_structure):
+            lsig[k] = np.log(np.var(ynp[col:col + width]))
+            col += width
+        self.lLmb.assign(np.tile(llmb, self.q).reshape(self.q, d))
+        self.lLmb0.assign(np.ones(self.q))
+        self.lnugGPs.assign(np.exp(-10.0) * np.ones(self.q))
+        self.lsigma2s.assign(lsig)
+
+    @property
+    def trainable_variables(self):
+        # attribute-name order of the reference's tf.Module: lLmb, lLmb0, lnugGPs, lsigma2s
+        return [self.lLmb.unconstrained, self.lLmb0.unconstrained, self.lnugGPs.unconstrained,
+                self.lsigma2s.unconstrained]
+
+    def _get_param_graph(self):
+        reps = torch.as_tensor(self.diag_error_structure, dtype=torch.long)
+        return (self.lLmb.value(), self.lLmb0.value(),
+                torch.repeat_interleave(self.lsigma2s.value(), reps), self.lnugGPs.value())
+
+    def get_param(self):
+        """lcgp.py:515-532: (lLmb, lLmb0, lsigma2s expanded to a p-vector, lnugGPs), detached."""
+        return tuple(t.detach() for t in self._get_param_graph())
+
+    # ------------------------------------------------------------------ engine
+    def _problem_data(self):
+        """Constant arrays of the objective in the form the C-ABI takes (include/lcgp_b200.h)."""
+        if self.submethod == 'rep':
+            r = self.r.to(DT)
+            X = self.x_unique_s
+            Ybar = self.ybar_s if self.rep_standardize_ybar else self.ybar
+            t = self.ybar_std[:, 0] if self.rep_standardize_ybar else torch.ones(int(self.p), dtype=DT)
+            scale = 1.0 / float(self.n)
+        else:
+            r = torch.ones(int(self.n), dtype=DT)
+            X = self.x
+            Ybar = self.y
+            t = torch.ones(int(self.p), dtype=DT)
+            scale = 1.0
+        YR = Ybar * r[None, :]
+        return dict(n=int(self.n), d=int(self.d), p=int(self.p), X=X, sr=torch.sqrt(r), YR=YR,
+                    w=(YR * Ybar).sum(dim=1), t=t, scale=scale, sum_log_r=float(torch.log(r).sum()))
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            data = self._problem_data()
+            idx = self._local_idx
+            if idx.numel() == 0:
+                self._engine = False      # this rank owns no latent
+            else:
+                factory = self._engine_factory or CudaEngine
+                kw = {} if self._engine_factory else dict(device=self._device)
+                self._engine = factory(phi_loc=self.phi[:, idx], D_loc=self.diag_D[idx],
+                                       include_host_terms=(self._rank == 0), **data, **kw)
+        return self._engine
+
+    def _evaluate(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
+        """All-latent objective (+ gradient wrt the constrained values) as CPU tensors."""
+        q, d, p = int(self.q), int(self.d), int(self.p)
+        idx = self._local_idx
+        eng = self.engine
+        self.n_evals += 1
+        if self._world == 1:
+            out = eng.evaluate(lLmb, lLmb0, lnug, lsig_p, need_grad, events)
+            ql = q
+            flat = out[:1 + p + ql * d + 2 * ql]
+        else:
+            ql = idx.numel()
+            nflat = 1 + p + q * d + 2 * q
+            if eng is False:
+                flat = torch.zeros(nflat, dtype=DT, device=self._collective_device())
+            else:
+                dev_eval = getattr(eng, 'evaluate_device', None)
+                out = dev_eval(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events) if dev_eval \
+                    else eng.evaluate(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
+                flat = torch.zeros(nflat, dtype=DT, device=out.device)
+                flat[:1 + p] = out[:1 + p]
+                if need_grad:
+                    o = 1 + p
+                    di = idx.to(out.device)
+                    flat[o:o + q * d].view(q, d)[di] = out[o:o + ql * d].view(ql, d)
+                    flat[o + q * d:o + q * d + q][di] = out[o + ql * d:o + ql * d + ql]
+                    flat[o + q * d + q:o + q * d + 2 * q][di] = out[o + ql * d + ql:o + ql * d + 2 * ql]
+            torch.distributed.all_reduce(flat)
+            if flat.is_cuda and eng is not False and hasattr(eng, 'd_info'):
+                info = eng.d_info.cpu()
+                eng._check_info(info)
+            flat = flat.cpu()
+        self._factor_key = self._key(lLmb, lLmb0, lsig_p, lnug)
+        val = flat[0].clone()
+        if not need_grad:
+            return val, None
+        o = 1 + p
+        return val, (flat[o:o + q * d].reshape(q, d).clone(), flat[o + q * d:o + q * d + q].clone(),
+                     flat[1:1 + p].clone(), flat[o + q * d + q:o + q * d + 2 * q].clone())
+
+    def _collective_device(self):
+        be = torch.distributed.get_backend()
+        return torch.device('cuda', torch.cuda.current_device()) if be == 'nccl' else torch.device('cpu')
+
+    @staticmethod
+    def _key(*ts):
+        return b''.join(t.detach().cpu().numpy().tobytes() for t in ts)
+
+    # ------------------------------------------------------------------ losses
+    def loss(self):
+        """lcgp.py:542-549."""
+        try:
+            return self.submethod_loss_map[self.submethod]()
+        except KeyError:
+            raise ValueError("Invalid submethod. Choices are 'full' or 'rep'.")
+
+    def _neglpost(self):
+        lLmb, lLmb0, lsig_p, lnug = self._get_param_graph()
+        return _NegLogPost.apply(self, lLmb, lLmb0, lsig_p, lnug)
+
+    def neglpost_rep(self):
+        """Replicated negative log posterior, divided by n (lcgp.py:554-630)."""
+        return self._neglpost()
+
+    def neglpost(self):
+        """Negative log posterior of the unreplicated model (lcgp.py:635-666)."""
+        return self._neglpost()
+
+    def loss_and_grad(self):
+        """(objective, flat gradient wrt the unconstrained variables in trainable_variables order)."""
+        tv = self.trainable_variables
+        for v in tv:
+            v.grad = None
+        val = self.loss()
+        val.backward()
+        return float(val.detach()), torch.cat([v.grad.reshape(-1) for v in tv]).numpy().copy()
+
+    def _flat_get(self):
+        return torch.cat([v.detach().reshape(-1) for v in self.trainable_variables]).numpy().copy()
+
+    def _flat_set(self, vec):
+        vec = torch.as_tensor(np.asarray(vec, dtype=np.float64), dtype=DT)
+        o = 0
+        with torch.no_grad():
+            for v in self.trainable_variables:
+                m = v.numel()
+                v.copy_(vec[o:o + m].reshape(v.shape))
+                o += m
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, verbose=False, optimizer: str = 'L-BFGS-B', **options):
+        """lcgp.py:537-540.  optimizer='L-BFGS-B' is SciPy's, as driven by gpflow.optimizers.Scipy in
+        the reference; optimizer='torch-lbfgs' is torch.optim.LBFGS with strong-Wolfe line search.
+        Both run on the host and call the CUDA objective once per closure evaluation."""
+        self._invalidate_aux()
+        if optimizer == 'L-BFGS-B':
+            import scipy.optimize
+
+            def fun(v):
+                self._flat_set(v)
+                f, g = self.loss_and_grad()
+                if verbose:
+                    print(f'  eval {self.n_evals}: loss {f:.10g}  |g| {np.linalg.norm(g):.3e}')
+                return f, g
+            res = scipy.optimize.minimize(fun, self._flat_get(), jac=True, method='L-BFGS-B',
+                                          options=options or None)
+            self._flat_set(res.x)
+            self.opt_result = res
+        elif optimizer == 'torch-lbfgs':
+            kw = dict(lr=1.0, max_iter=500, history_size=10, line_search_fn='strong_wolfe',
+                      tolerance_grad=1e-9, tolerance_change=1e-12)
+            kw.update(options)
+            opt = torch.optim.LBFGS(self.trainable_variables, **kw)
+
+            def closure():
+                opt.zero_grad()
+                val = self.loss()
+                val.backward()
+                return val
+            opt.step(closure)
+            self.opt_result = opt.state_dict()['state']
+        else:
+            raise ValueError("optimizer must be 'L-BFGS-B' or 'torch-lbfgs'")
+        self._invalidate_aux()
+        return
+
+    # ------------------------------------------------------------------ aux predictive quantities
+    def _invalidate_aux(self):
+        self._factor_key = None
+        self.CinvMs = torch.full((int(self.q), int(self.n)), float('nan'), dtype=DT)
+        self.mks = torch.full((int(self.q), int(self.n)), float('nan'), dtype=DT)
+        self.Tks = None
+        self.Ths = None
+
+    def _refresh_factor(self):
+        """Make sure the workspace holds the factor for the current parameters."""
+        lLmb, lLmb0, lsig_p, lnug = self.get_param()
+        if self._factor_key != self._key(lLmb, lLmb0, lsig_p, lnug):
+            self._evaluate(lLmb, lLmb0, lsig_p, lnug, need_grad=False)
+        return lLmb, lLmb0, lsig_p, lnug
+
+    def _gather_rows(self, local, width):
+        """(q_loc x width) per rank -> (q x width) on the CPU, rows placed by latent index."""
+        q = int(self.q)
+        if self._world == 1:
+            return local.cpu()
+        dev = self._collective_device()
+        full = torch.zeros((q, width), dtype=DT, device=dev)
+        if local is not None:
+            full[self._local_idx.to(dev)] = local.to(dev)
+        torch.distributed.all_reduce(full)
+        return full.cpu()
+
+    def compute_aux_predictive_quantities(self):
+        """lcgp.py:685-726 / 728-803: CinvMs (= alpha_k), mks (rep) and lazy Tks / Ths."""
+        self._refresh_factor()
+        eng = self.engine
+        a, m = eng.aux() if eng is not False else (None, None)
+        n = int(self.n)
+        self.CinvMs = self._gather_rows(a, n)
+        self.mks = self._gather_rows(m, n)
+        lsig_p = self.get_param()[2]
+        sinv = torch.exp(-0.5 * lsig_p)
+        if self.submethod == 'rep':
+            if self.rep_standardize_ybar:
+                sinv = sinv * self.ybar_std[:, 0]
+            q, p = int(self.q), int(self.p)
+            # lcgp.py:754 as coded broadcasts only for q == p (SURVEY B-3); otherwise divide columns
+            self.psi_c = self.phi.T / sinv[:, None] if (q == p or p == 1) else self.phi.T / sinv[None, :]
+            self.Tks = _LazyOperators(self, 'Tks')
+            self.Ths = None
+        else:
+            self.Ths = _LazyOperators(self, 'Ths')
+
+    def _compute_aux_predictive_quantities_rep(self):
+        self.compute_aux_predictive_quantities()
+
+    def _aux_is_stale(self):
+        return bool(torch.isnan(self.CinvMs).any()) or (self.Tks is None and self.Ths is None)
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, x0, return_fullcov=False):
+        """lcgp.py:671-680."""
+        x0 = _as_tensor2d(x0)
+        try:
+            call = self.submethod_predict_map[self.submethod]
+        except KeyError as e:
+            print(e)
+            raise KeyError('Invalid submethod.  Choices are \'full\' or \'rep\'.')
+        res = call(x0=x0, return_fullcov=return_fullcov)
+        return tuple(t.detach() if t is not None else None for t in res)
+
+    def _predict_latents(self, x0, Xtrain, chunk=2048):
+        if self._aux_is_stale():
+            self.compute_aux_predictive_quantities()
+        lLmb, lLmb0, lsig_p, lnug = self._refresh_factor()
+        x0s = (x0 - self.x_min) / (self.x_max - self.x_min)                 # lcgp.py:822 / :877
+        same = x0s.shape == Xtrain.shape and bool(torch.equal(x0s, Xtrain))  # covmat.py:46-49
+        idx = self._local_idx
+        eng = self.engine
+        n0 = int(x0s.shape[0])
+        if same:
+            chunk = n0    # the nugget-on-the-diagonal quirk needs global row indices
+        gh, gv = [], []
+        for s in range(0, n0, chunk):
+            if eng is not False:
+                a, b = eng.predict_latents(lLmb[idx], lLmb0[idx], lnug[idx], x0s[s:s + chunk].contiguous(), same)
+            else:
+                a = b = None
+            w = min(chunk, n0 - s)
+            gh.append(self._gather_rows(a, w))
+            gv.append(self._gather_rows(b, w))
+        self.ghat = torch.cat(gh, dim=1)
+        self.gvar = torch.cat(gv, dim=1)
+        return self.ghat, self.gvar, lsig_p
+
+    def predict_full(self, x0, return_fullcov=False):
+        """lcgp.py:808-859."""
+        ghat, gvar, lsig_p = self._predict_latents(x0, self.x)
+        psi = self.phi.T * torch.sqrt(torch.exp(lsig_p))                    # (q, p)
+        predmean = psi.T @ ghat
+        confvar = gvar.T @ psi ** 2
+        predvar = confvar + torch.exp(lsig_p)
+        ypred = self.tx_y(predmean)
+        yconfvar = confvar.T * self.ystd ** 2
+        ypredvar = predvar.T * self.ystd ** 2
+        if return_fullcov:
+            CH = torch.einsum('kn,kp->npk', torch.sqrt(gvar), psi)
+            full = CH @ CH.transpose(1, 2) + torch.diag(torch.exp(lsig_p))[None]
+            sv = self.ystd[:, 0]
+            full = full * (sv[:, None] * sv[None, :])[None]
+            return ypred, ypredvar, yconfvar, full
+        return ypred, ypredvar, yconfvar
+
+    def predict_rep(self, x0, return_fullcov=False):
+        """lcgp.py:864-930."""
+        ghat, gvar, lsig_p = self._predict_latents(x0, self.x_unique_s)
+        sigma_var = torch.exp(lsig_p)
+        sigma_sqrt = torch.sqrt(sigma_var)
+        if self.rep_standardize_ybar:
+            std = self.ybar_std[:, 0]
+            sigma_sqrt = sigma_sqrt / std
+            sigma_var = sigma_var / std ** 2
+        Psi = self.phi * sigma_sqrt[:, None]
+        predmean = Psi @ ghat
+        confvar = (Psi ** 2) @ gvar
+        predvar = confvar + sigma_var[:, None]
+        if self.rep_standardize_ybar:
+            ypred = predmean * self.ybar_std + self.ybar_mean
+            yconfvar = confvar * self.ybar_std ** 2
+            ypredvar = predvar * self.ybar_std ** 2
+        else:
+            ypred, yconfvar, ypredvar = predmean, confvar, predvar
+        if return_fullcov:
+            return ypred, ypredvar, yconfvar, None
+        return ypred, ypredvar, yconfvar
+
+
+class _LazyDiag:
+    """diag(r) (lcgp.py:378) without the n x n allocation until someone asks for it."""
+
+    def __init__(self, r):
+        self._r = r
+        self.shape = (r.shape[0], r.shape[0])
+
+    def materialize(self):
+        return torch.diag(self._r.to(DT))
+
+    def numpy(self):
+        return self.materialize().numpy()
+
+
+class _LazyOperators:
+    """Stand-in for the reference's q x n x n `Tks` / `Ths` tensors (lcgp.py:760, 700): 16 GB at
+    n = 8000, q = 32.  Indexing with k rebuilds operator k from the factor in the workspace:
+    Tks[k] = d_k (sqrt r sqrt r^T) o A_k^{-1}   (== C^-1 - C^-1 (C^-1 + d_k R)^-1 C^-1, lcgp.py:783-788)
+    Ths[k] = sqrt(d_k) L_k^{-T}                 (Th Th^T == (C_k + I/d_k)^{-1} as in lcgp.py:709-715)"""
+
+    def __init__(self, model, kind):
+        self._m, self._kind = model, kind
+        self.shape = (int(model.q), int(model.n), int(model.n))
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, k):
+        m = self._m
+        k = int(k)
+        if m._world != 1:
+            raise NotImplementedError('dense Tks/Ths are only materialised in single-rank mode')
+        m._refresh_factor()
+        Ainv = m.engine.ainv(k).cpu()
+        dk = m.diag_D[k]
+        if self._kind == 'Tks':
+            sr = torch.sqrt(m.r.to(DT))
+            return dk * (sr[:, None] * sr[None, :]) * Ainv
+        # symmetric square root is not unique; return the Cholesky-type factor of d_k A^{-1}
+        return torch.linalg.cholesky(dk * Ainv)
+
+    def numpy(self):
+        return torch.stack([self[k] for k in range(self.shape[0])]).numpy()
