@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the LCGP emulator-fitting hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4_rep] [--impl ours|reference]
+
+A "step" is one objective + analytic-gradient evaluation over all q latents at the `init_params`
+point of the named synthetic configuration (default: BASELINE.json config 4, n=8000, d=10, p=2000,
+q=32, replicated data).  For N > 1 launch under torchrun; the latents are sharded over the ranks and
+each step ends with the all-reduce of the objective / gradient, so `value` is whole-job evals/s
+(total work fixed as N grows: "strong" scaling).
+
+  value : K device-resident steps (parameters already in HBM, no host copies) timed with CUDA events
+  e2e   : K steps through LCGP.loss_and_grad() -- host parameters in, host objective + gradient out
+  roofline / stages : per-stage CUDA-event times recorded inside the C-ABI call on its stream
+  cpu_baseline : the torch-float64 oracle timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='cfg4_rep')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-latents', type=int, default=1)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'power_w_max': float(max(pw)),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def dgemm_peak(device, n=6144, reps=4):
+    """cuBLAS DGEMM throughput on this GPU (burst, best of reps): the FP64 tensor-pipe denominator."""
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def build_model(cfg_name):
+    from lcgp_b200 import LCGP, synthetic
+    x, y, x0, y0, mk = synthetic.make_config(cfg_name)
+    t0 = time.time()
+    model = LCGP(y=y, x=x, **mk)
+    return model, time.time() - t0, (x, y, mk)
+
+
+def workload_desc(cfg_name, model):
+    return {'workload': f'{cfg_name}: objective+gradient, n={int(model.n)} unique inputs, d={int(model.d)}, '
+                        f'p={int(model.p)}, q={int(model.q)}, submethod={model.submethod}, init_params point',
+            'n': int(model.n), 'd': int(model.d), 'p': int(model.p), 'q': int(model.q),
+            'l2': 'inputs larger than L2 (factor buffers %.1f GB per rank)' % (
+                len(model._local_idx) * (((int(model.n) + 127) // 128 * 128) ** 2) * 8 / 1e9)}
+
+
+def cpu_baseline_sample(x, y, mk, n_latents, q, threads):
+    """Oracle (torch float64 CPU, autograd) on `n_latents` of the q latents at full n; evals/s
+    extrapolated as 1 / (q/n_latents * t).  Returns (evals_per_s, seconds, description)."""
+    from oracle.lcgp_oracle import LCGPOracle
+    import psutil
+    torch.set_num_threads(threads)
+    n_unique = np.unique(x, axis=0).shape[0] if mk['submethod'] == 'rep' else x.shape[0]
+    need = (4 * x.shape[1] + 12) * n_unique * n_unique * 8 * n_latents   # autograd keeps ~4 n x n per input dim
+    if need > 0.6 * psutil.virtual_memory().available:
+        raise MemoryError(f'oracle sample needs ~{need / 1e9:.0f} GB of host memory')
+    o = LCGPOracle(y=y, x=x, skip_xnorm=True, **mk)
+    lat = list(range(n_latents))
+    fn = (lambda: o.neglpost_rep(latents=lat)) if mk['submethod'] == 'rep' else None
+    if fn is None:
+        fn = lambda: o.neglpost_chol(latents=lat)
+    t0 = time.time()
+    o.loss_and_grad(fn)
+    dt = time.time() - t0
+    return o, fn, dt
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of the reference's CPU path on this box's host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from lcgp_b200 import synthetic
+    threads = os.cpu_count() or 1
+    x, y, x0, y0, mk = synthetic.make_config(args.config)
+    o, fn, first = cpu_baseline_sample(x, y, mk, args.cpu_sample_latents, mk['q'], threads)
+    q = int(mk['q'])
+    for _ in range(max(args.warmup - 1, 0)):
+        o.loss_and_grad(fn)
+    t0 = time.time()
+    for _ in range(args.steps):
+        o.loss_and_grad(fn)
+    dt = (time.time() - t0) / args.steps
+    per_eval = dt * q / args.cpu_sample_latents
+    val = 1.0 / per_eval
+    sample = (f'{args.cpu_sample_latents} of {q} latents per step at full n (forward + autograd backward), '
+              f'extrapolated x{q // args.cpu_sample_latents}')
+    line = {'impl': 'reference', 'metric': 'NLL+grad evals/s', 'value': val, 'unit': 'evals/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_eval * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'{args.config}: objective+gradient (oracle port of the reference CPU path)',
+                       'n': int(o.n), 'd': int(o.d), 'p': int(o.p), 'q': q},
+            'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (B200); there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from lcgp_b200 import _cabi
+
+    model, t_ctor, (x, y, mk) = build_model(args.config)
+    eng = model.engine
+    q, d, p, n = int(model.q), int(model.d), int(model.p), int(model.n)
+    q_loc = len(model._local_idx)
+    lLmb, lLmb0, lsig_p, lnug = model.get_param()
+    idx = model._local_idx
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(events=None):
+        # N = 1: one lcgp_nll_grad call, parameters and results stay in HBM.
+        # N > 1: the same on each rank's latents + the single flat all-reduce (model._evaluate_sharded).
+        if world > 1:
+            return model._evaluate_sharded(lLmb, lLmb0, lsig_p, lnug, True, events)
+        return eng.evaluate_device(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, True, events)
+
+    # ---- warm-up (also through the public API) ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    model.loss_and_grad()
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+
+    # ---- value: device-resident steps, CUDA events on the launching stream ----
+    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    for evs in stage_ev:
+        for e in evs:
+            e.record()          # force creation of the underlying cudaEvent_t
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        device_step(stage_ev[s])
+    e1.record()
+    barrier()
+    t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    stages = np.array([[evs[i].elapsed_time(evs[i + 1]) for i in range(4)] for evs in stage_ev]).mean(axis=0)  # ms
+    st = torch.tensor(stages, dtype=torch.float64, device=dev)
+
+    # ---- e2e: public API, host parameters in, host objective + gradient out ----
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        f_e2e, g_e2e = model.loss_and_grad()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        torch.distributed.all_reduce(t_dev, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(st, op=torch.distributed.ReduceOp.MAX)
+    clk = clocks.stop() if rank == 0 else None
+    t_dev, t_e2e, stages = float(t_dev), float(t_e2e), st.cpu().numpy()
+
+    if rank == 0:
+        peaks, psrc = measured_peaks()
+        fp64_peak = dgemm_peak(dev)
+        npad = _cabi.padded(n)
+        chol_flops = q_loc * n ** 3 / 3.0              # algorithmic, per launch of the Cholesky stage on one rank
+        chol_tf = chol_flops / (stages[1] * 1e-3) / 1e12
+        build_bytes = 8.0 * q_loc * n * (n + 1) / 2     # lower triangle written
+        line = {
+            'metric': 'NLL+grad evals/s', 'value': args.steps / t_dev, 'unit': 'evals/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_dev / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_desc(args.config, model), parallelism=f'latents sharded over {world} rank(s)'),
+            'e2e': {'value': args.steps / t_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': eng.h2d_bytes,
+                    'd2h_bytes_per_step': eng.d2h_bytes if world == 1 else (1 + p + q * d + 2 * q) * 8},
+            'gpu_launches': eng.launches_per_eval * args.steps,
+            'roofline': {'bound': 'tensor', 'kernel': 'batched blocked Cholesky stage (DMMA SYRK/TRSM GEMM + diagonal-block kernel)',
+                         'achieved': chol_tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': chol_tf / fp64_peak,
+                         'peak_source': 'cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
+                         'flops_per_launch': chol_flops, 'traffic': None},
+            'stages': {
+                'build_ms': float(stages[0]), 'cholesky_ms': float(stages[1]), 'trtri_ms': float(stages[2]),
+                'solve_contract_ms': float(stages[3]),
+                'build_gbs': build_bytes / (stages[0] * 1e-3) / 1e9, 'hbm_peak_gbs': peaks['hbm_gbs'],
+                'hbm_peak_source': psrc, 'build_frac_of_hbm': build_bytes / (stages[0] * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'cholesky_tflops': chol_tf, 'trtri_tflops': q_loc * n ** 3 / 3.0 / (stages[2] * 1e-3) / 1e12,
+                'contract_tflops': q_loc * n ** 3 / 3.0 / (stages[3] * 1e-3) / 1e12,
+                'whole_eval_tflops': q_loc * float(n) ** 3 / (t_dev / args.steps) / 1e12,
+                'padded_n': npad},
+            'clocks': clk, 'objective': f_e2e, 'grad_norm': float(np.linalg.norm(g_e2e)), 'ctor_s': t_ctor,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            try:
+                _, _, dt = cpu_baseline_sample(x, y, mk, args.cpu_sample_latents, q, threads)
+                per_eval = dt * q / args.cpu_sample_latents
+                line['cpu_baseline'] = {'value': 1.0 / per_eval, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+                                        'sample': f'{args.cpu_sample_latents} of {q} latents at full n, forward + autograd '
+                                                  f'backward, 1 repetition ({dt:.1f} s), extrapolated x{q // args.cpu_sample_latents}'}
+            except Exception as ex:   # baseline is informational; never lose the GPU numbers
+                line['cpu_baseline'] = {'value': None, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+                                        'sample': f'failed: {ex!r}'}
+        else:
+            line['cpu_baseline'] = None
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

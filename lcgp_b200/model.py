@@ -523,37 +523,43 @@ class LCGP:
                                        include_host_terms=(self._rank == 0), **data, **kw)
         return self._engine
 
-    def _evaluate(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
-        """All-latent objective (+ gradient wrt the constrained values) as CPU tensors."""
+    def _evaluate_sharded(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
+        """Multi-rank evaluation: local latents on this rank's engine, then ONE all-reduce of the flat
+        vector [objective | d/d lsigma2 (p) | d/d lLmb (q x d) | d/d lLmb0 (q) | d/d lnugGPs (q)]
+        (each rank fills only its own latents' rows).  Returns the reduced vector on the collective
+        device without synchronising the host."""
         q, d, p = int(self.q), int(self.d), int(self.p)
         idx = self._local_idx
         eng = self.engine
+        ql = idx.numel()
+        nflat = 1 + p + q * d + 2 * q
+        if eng is False:
+            flat = torch.zeros(nflat, dtype=DT, device=self._collective_device())
+        else:
+            dev_eval = getattr(eng, 'evaluate_device', None) or eng.evaluate
+            out = dev_eval(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
+            flat = torch.zeros(nflat, dtype=DT, device=out.device)
+            flat[:1 + p] = out[:1 + p]
+            if need_grad:
+                o = 1 + p
+                di = idx.to(out.device)
+                flat[o:o + q * d].view(q, d)[di] = out[o:o + ql * d].view(ql, d)
+                flat[o + q * d:o + q * d + q][di] = out[o + ql * d:o + ql * d + ql]
+                flat[o + q * d + q:o + q * d + 2 * q][di] = out[o + ql * d + ql:o + ql * d + 2 * ql]
+        torch.distributed.all_reduce(flat)
+        return flat
+
+    def _evaluate(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
+        """All-latent objective (+ gradient wrt the constrained values) as CPU tensors."""
+        q, d, p = int(self.q), int(self.d), int(self.p)
+        eng = self.engine
         self.n_evals += 1
         if self._world == 1:
-            out = eng.evaluate(lLmb, lLmb0, lnug, lsig_p, need_grad, events)
-            ql = q
-            flat = out[:1 + p + ql * d + 2 * ql]
+            flat = eng.evaluate(lLmb, lLmb0, lnug, lsig_p, need_grad, events)[:1 + p + q * d + 2 * q]
         else:
-            ql = idx.numel()
-            nflat = 1 + p + q * d + 2 * q
-            if eng is False:
-                flat = torch.zeros(nflat, dtype=DT, device=self._collective_device())
-            else:
-                dev_eval = getattr(eng, 'evaluate_device', None)
-                out = dev_eval(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events) if dev_eval \
-                    else eng.evaluate(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
-                flat = torch.zeros(nflat, dtype=DT, device=out.device)
-                flat[:1 + p] = out[:1 + p]
-                if need_grad:
-                    o = 1 + p
-                    di = idx.to(out.device)
-                    flat[o:o + q * d].view(q, d)[di] = out[o:o + ql * d].view(ql, d)
-                    flat[o + q * d:o + q * d + q][di] = out[o + ql * d:o + ql * d + ql]
-                    flat[o + q * d + q:o + q * d + 2 * q][di] = out[o + ql * d + ql:o + ql * d + 2 * ql]
-            torch.distributed.all_reduce(flat)
+            flat = self._evaluate_sharded(lLmb, lLmb0, lsig_p, lnug, need_grad, events)
             if flat.is_cuda and eng is not False and hasattr(eng, 'd_info'):
-                info = eng.d_info.cpu()
-                eng._check_info(info)
+                eng._check_info(eng.d_info.cpu())
             flat = flat.cpu()
         self._factor_key = self._key(lLmb, lLmb0, lsig_p, lnug)
         val = flat[0].clone()

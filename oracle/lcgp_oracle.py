@@ -124,7 +124,10 @@ class LCGPOracle:
     def __init__(self, y=None, x=None, q: int = None, var_threshold: float = None,
                  diag_error_structure: list = None, parameter_clamp_flag: bool = False,
                  robust_mean: bool = True, submethod: str = 'full',
-                 rep_standardize_ybar: bool = True, verbose: bool = False):
+                 rep_standardize_ybar: bool = True, verbose: bool = False, skip_xnorm: bool = False):
+        # skip_xnorm: do not evaluate the dead O(N^2 d) `xnorm` statistic of init_standard_x
+        # (lcgp.py:304-309; unused by the model) -- only for the large bench configurations.
+        self._skip_xnorm = skip_xnorm
         # lcgp.py:52-55
         self.verbose = verbose
         self.robust_mean = robust_mean
@@ -150,7 +153,7 @@ class LCGPOracle:
         self.x_orig = self.x
         self.y_orig = self.y
         # :97
-        self.x, self.x_min, self.x_max, _, self.xnorm = self.init_standard_x(self.x)
+        self.x, self.x_min, self.x_max, _, self.xnorm = self.init_standard_x(self.x, skip_xnorm)
         self._rep_initialized = False
 
         if self.submethod == 'rep':                                    # :105-150
@@ -221,12 +224,12 @@ class LCGPOracle:
         return ys * self.ystd + self.ymean
 
     @staticmethod
-    def init_standard_x(x):                                            # :295-310
+    def init_standard_x(x, skip_xnorm=False):                          # :295-310
         x_max = x.max(dim=0).values
         x_min = x.min(dim=0).values
         xs = (x - x_min) / (x_max - x_min)
         xnorm = torch.zeros(x.shape[1], dtype=DT)
-        for j in range(x.shape[1]):
+        for j in range(0 if skip_xnorm else x.shape[1]):
             xdist = torch.abs(x[:, j].reshape(-1, 1) - x[:, j])
             xnorm[j] = xdist[xdist > 0].mean()
         return xs, x_min, x_max, x, xnorm
@@ -333,7 +336,8 @@ class LCGPOracle:
         except KeyError:
             raise ValueError("Invalid submethod. Choices are 'full' or 'rep'.")
 
-    def neglpost_rep(self):                                            # :554-630
+    def neglpost_rep(self, latents=None):                              # :554-630
+        # `latents`: optional subset of k (bench.py times a bounded sample of the q-loop); None = all
         lLmb, lLmb0, lsigma2s, lnugGPs = self.get_param()
         xk = self.x_unique_s
         r = self.r.to(DT)
@@ -362,7 +366,7 @@ class LCGPOracle:
         bkSb_sum = torch.zeros((), dtype=DT)
         logA_sum = torch.zeros((), dtype=DT)
         eye = torch.eye(int(self.n), dtype=DT)
-        for k in range(int(self.q)):                                   # :605-624
+        for k in (range(int(self.q)) if latents is None else latents):  # :605-624
             Ck = Matern32(xk, xk, llmb=lLmb[k], llmb0=lLmb0[k], lnug=lnugGPs[k])
             b_k = r * (ybar.T @ (sigma_inv_sqrt * phi[:, k]))          # :608-610
             d_k = D[k]
@@ -399,7 +403,7 @@ class LCGPOracle:
         nlp = nlp + 0.5 * ((y.T / torch.sqrt(torch.exp(lsigma2s))) ** 2).sum()   # :664
         return nlp
 
-    def neglpost_chol(self):
+    def neglpost_chol(self, latents=None):
         """Full-mode objective in single-Cholesky form: algebraically identical to
         `neglpost` (eigh form) but O(n^3/3) per latent; used as the oracle at sizes where eigh +
         autograd is too slow.  Checked against `neglpost` in tests/test_oracle_selfcheck.py."""
@@ -410,7 +414,7 @@ class LCGPOracle:
         sinv = torch.exp(-0.5 * lsigma2s)
         eye = torch.eye(int(self.n), dtype=DT)
         nlp = torch.zeros((), dtype=DT)
-        for k in range(int(self.q)):
+        for k in (range(int(self.q)) if latents is None else latents):
             Ck = Matern32(x, x, llmb=lLmb[k], llmb0=lLmb0[k], lnug=lnugGPs[k])
             b = y.T @ (sinv * phi[:, k])
             LA = torch.linalg.cholesky(eye + D[k] * Ck)
