@@ -10,81 +10,110 @@
 namespace lcgp {
 
 // ------------------------------------------------------------------------------------------
-// Diagonal-block kernel: one CTA per matrix.  The block lives in shared memory as S[128][129]:
-// the lower triangle is the running Schur complement / L, the strictly-upper triangle holds the
-// transpose of the running inverse Z (Z[i][j] at S[j][i]); zd[] is the diagonal of Z.  Column
-// step c scales column c by 1/L_cc (which finalises both column c of L and row c of Z) and then
-// applies one rank-1 update that serves the Cholesky trailing block and the forward elimination
-// of the identity at the same time.
+// Diagonal-block kernel: one CTA (16 x 16 threads) per matrix; the 128 x 128 block is REGISTER
+// resident, thread (ty, tx) owning S[ty + 16 i][tx + 16 j], i, j < 8.  The lower triangle is the
+// running Schur complement, the strictly-upper triangle the transpose of the running inverse Z of
+// the factor (Z[i][j] at S[j][i]).  Column step c: the 16 owners of column c publish it (u, with
+// u[c] := 1) and the pivot to shared memory, ONE barrier, then every thread applies
+//     S[a][b] -= u[a] u[b] / piv     for  b > c  and  (a >= b  or  a <= c)
+// which is at once the Cholesky trailing update and the forward elimination of the identity.
+// Column c is dead afterwards, so its scaling by 1/sqrt(piv_c) is deferred to the write-back
+// (L[a][c] = u[a]/sqrt(piv_c), Z[c][a] likewise).  u / piv are double-buffered by the parity of c,
+// which is what makes a single barrier per column sufficient.  The loop over the 16-column groups
+// is unrolled so that every ownership test on (i, j) folds at compile time.
 // ------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
 constexpr int DPITCH = NB + 1;
-constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 3 * NB + 8);
+constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 2 * NB + NB + NB + 8);
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet_part /* [batch][nb] */,
                   int* info /* [batch] */) {
     extern __shared__ __align__(16) double sm[];
-    double* S = sm;
-    double* cv = sm + NB * DPITCH;   // scaled column c (cv[c] = 1/L_cc)
-    double* zd = cv + NB;            // diagonal of the inverse
-    double* ldg = zd + NB;           // diagonal of L
-    double* red = ldg + NB;
+    double* S = sm;                     // write-back staging only
+    double* ucol = sm + NB * DPITCH;    // [2][NB]
+    double* pivs = ucol + 2 * NB;       // pivots of all columns
+    double* invd = pivs + NB;           // 1 / L_cc
+    double* red = invd + NB;
     const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
     const int bz = blockIdx.x;
     double* blk = v.F + (size_t)bz * v.fstride + (size_t)jb * NB * v.np + (size_t)jb * NB;
 
-    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        S[r * DPITCH + c] = (c <= r) ? blk[(size_t)r * v.np + c] : 0.0;
+    double reg[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = ty + 16 * i, b = tx + 16 * j;
+            reg[i][j] = (a >= b) ? blk[(size_t)a * v.np + b] : 0.0;
+        }
+    const bool p_low = ty >= tx;
+
+#pragma unroll
+    for (int jc = 0; jc < 8; ++jc) {
+        for (int cc = 0; cc < 16; ++cc) {
+            const int c = jc * 16 + cc;
+            double* ub_ = ucol + (c & 1) * NB;
+            if (tx == cc) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int a = ty + 16 * i;
+                    if (i == jc && ty == cc) { pivs[c] = reg[i][jc]; ub_[a] = 1.0; }
+                    else ub_[a] = reg[i][jc];
+                }
+            }
+            __syncthreads();
+            const double piv = pivs[c];
+            const double ipiv = 1.0 / piv;
+            double ua[8], ub[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ua[i] = ub_[ty + 16 * i] * ipiv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ub[j] = ub_[tx + 16 * j];
+            const bool p_bgt = tx > cc, p_ale = ty <= cc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool lower = (i > j) || (i == j && p_low);
+                    const bool b_gt = (j > jc) || (j == jc && p_bgt);
+                    const bool a_le = (i < jc) || (i == jc && p_ale);
+                    if (b_gt && (lower || a_le)) reg[i][j] -= ua[i] * ub[j];
+                }
+        }
     }
     __syncthreads();
-
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int c = 0; c < NB; ++c) {
-        // S[c][c] is final after the barrier that closed step c-1 and is never written during
-        // step c (the diagonal of L is kept in ldg[] until write-back), so no barrier is needed
-        // between this read and the column scaling below.
-        const double piv = S[c * DPITCH + c];
-        if (!(piv > 0.0) && tid == 0) atomicCAS(&info[bz], 0, jb * NB + c + 1);
-        const double dd = sqrt(piv);
-        const double invd = 1.0 / dd;
-        if (tid < NB) {
-            const int r = tid;
-            if (r == c) {
-                ldg[c] = dd;
-                cv[c] = invd;
-                zd[c] = invd;
-            } else {
-                const double val = S[r * DPITCH + c] * invd;
-                S[r * DPITCH + c] = val;
-                cv[r] = val;
-            }
-        }
-        __syncthreads();
-        // rank-1 update: for i > c, rho <= i :  T(i,rho) -= cv[i] * cv[rho]
-        //   T(i,rho) = S[i][rho] if rho > c (Schur complement),  S[rho][i] if rho <= c (inverse^T)
-        for (int i = c + 1 + warp; i < NB; i += DIAG_THREADS / 32) {
-            const double li = cv[i];
-            for (int rho = lane; rho <= i; rho += 32) {
-                const int off = (rho > c) ? (i * DPITCH + rho) : (rho * DPITCH + i);
-                S[off] -= li * cv[rho];
-            }
-        }
-        __syncthreads();
+    if (tid < NB) {
+        const double piv = pivs[tid];
+        invd[tid] = 1.0 / sqrt(piv);
     }
+    __syncthreads();
+    // first bad pivot (if any), LAPACK style
+    if (tid == 0) {
+        for (int c = 0; c < NB; ++c)
+            if (!(pivs[c] > 0.0)) { atomicCAS(&info[bz], 0, jb * NB + c + 1); break; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = ty + 16 * i, b = tx + 16 * j;
+            S[a * DPITCH + b] = (a == b) ? sqrt(pivs[a]) : reg[i][j] * invd[b];
+        }
+    __syncthreads();
 
     // write back L (lower triangle only), DL = Z, DU = Z^T
     double* dl = DLw + (size_t)bz * v.dstride + (size_t)jb * NB * NB;
     double* du = DUw + (size_t)bz * v.dstride + (size_t)jb * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
         const int r = idx >> 7, c = idx & (NB - 1);
-        if (c <= r) blk[(size_t)r * v.np + c] = (c == r) ? ldg[r] : S[r * DPITCH + c];
-        dl[idx] = (c < r) ? S[c * DPITCH + r] : (c == r ? zd[r] : 0.0);
-        du[idx] = (c > r) ? S[r * DPITCH + c] : (c == r ? zd[r] : 0.0);
+        if (c <= r) blk[(size_t)r * v.np + c] = S[r * DPITCH + c];
+        dl[idx] = (c < r) ? S[c * DPITCH + r] : (c == r ? invd[r] : 0.0);
+        du[idx] = (c > r) ? S[r * DPITCH + c] : (c == r ? invd[r] : 0.0);
     }
-    // log det part: sum_c log L_cc = -sum_c log zd[c]
-    double lg = (tid < NB) ? -log(zd[tid]) : 0.0;
+    // log det part: sum_c log L_cc = 1/2 sum_c log piv_c
+    double lg = (tid < NB) ? 0.5 * log(pivs[tid]) : 0.0;
     lg = block_sum(lg, red);
     if (tid == 0 && logdet_part) logdet_part[(size_t)bz * v.nb + jb] = lg;
 }

@@ -1,0 +1,353 @@
+"""Parity of the CUDA path (through the C-ABI, as lcgp_b200.LCGP / Matern32 call it) against the CPU
+oracle on identical inputs.  Tolerances are BASELINE.json's: objective 1e-10 relative, gradients 1e-8,
+fitted hyper-parameters and predictions 1e-6."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lcgp_b200 import LCGP, Matern32, _cabi, evaluation, synthetic
+from oracle import lcgp_oracle as O
+from helpers import make_full_data, make_ragged_rep_data, make_rep_data, move_params
+
+pytestmark = pytest.mark.gpu
+DT = torch.float64
+NLL_TOL, GRAD_TOL, PRED_TOL = 1e-10, 1e-8, 1e-6
+HERE = os.path.dirname(__file__)
+FIX = json.load(open(os.path.join(HERE, 'golden', 'oracle_fixtures.json')))
+GOLD = json.load(open(os.path.join(HERE, 'golden', 'notebook_case2.json')))
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# ---------------------------------------------------------------- a1: kernel matrix
+@pytest.mark.parametrize('n1,n2,d', [(1, 1, 1), (7, 5, 1), (64, 64, 2), (65, 130, 3), (300, 300, 8), (129, 40, 10)])
+def test_matern32_matches_oracle(n1, n2, d):
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    x1 = torch.as_tensor(rng.uniform(0, 1, (n1, d)))
+    x2 = x1.clone() if n1 == n2 else torch.as_tensor(rng.uniform(0, 1, (n2, d)))
+    ell = torch.as_tensor(rng.uniform(0.2, 2.0, d)); s0 = torch.tensor(1.7, dtype=DT); nug = torch.tensor(3e-4, dtype=DT)
+    C = Matern32(x1, x2, ell, s0, nug)
+    Co = O.Matern32(x1, x2, ell, s0, nug)
+    assert C.shape == (n1, n2) and C.device.type == 'cpu'
+    assert rel(C, Co) < 1e-13                          # nugget only when the point sets are identical
+    if n1 == n2 and n1 > 1:
+        x2b = x2.clone(); x2b[0, 0] += 1e-3             # same shape, different values: no nugget
+        assert rel(Matern32(x1, x2b, ell, s0, nug), O.Matern32(x1, x2b, ell, s0, nug)) < 1e-13
+
+
+def test_matern32_argument_checks():                    # test_cov.py:18-23, covmat.py:18-29
+    x = torch.rand(5, 2, dtype=DT)
+    with pytest.raises(AssertionError):
+        Matern32(torch.rand(5, dtype=DT), x, torch.ones(2), 1.0, 1e-3)
+    with pytest.raises(AssertionError):
+        Matern32(x, torch.rand(5, 3, dtype=DT), torch.ones(2), 1.0, 1e-3)
+    with pytest.raises(AssertionError):
+        Matern32(x, x + 1.0, torch.ones(2), 1.0, 1e-3, diag_only=True)
+    assert torch.equal(Matern32(x, x, torch.ones(2), 2.5, 1e-3, diag_only=True), 2.5 * torch.ones(5, dtype=DT))
+
+
+# ---------------------------------------------------------------- stages through the C-ABI
+@pytest.mark.parametrize('n,d,q', [(40, 1, 2), (128, 2, 1), (129, 3, 2), (700, 5, 3), (1500, 8, 2)])
+def test_build_potrf_trtri_stages(n, d, q):
+    L = _cabi.lib()
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(n)
+    X = torch.as_tensor(rng.uniform(0, 1, (n, d))); r = torch.as_tensor(rng.integers(1, 4, n).astype(float))
+    sr = torch.sqrt(r)
+    ell = torch.as_tensor(rng.uniform(0.3, 1.5, (q, d))); s0 = torch.as_tensor(rng.uniform(0.5, 3, q))
+    nug = torch.as_tensor(np.exp(rng.uniform(-12, -5, q))); D = torch.as_tensor(rng.uniform(0.3, 2, q))
+    npad = _cabi.padded(n); nb = npad // 128; st = _cabi.stream_ptr()
+    g = lambda t: t.to(dev).contiguous()
+    Xd, srd, elld, s0d, nugd, Dd = map(g, (X, sr, ell, s0, nug, D))
+    F = torch.full((q, npad, npad), float('nan'), dtype=DT, device=dev)
+    assert L.lcgp_build_A(Xd.data_ptr(), srd.data_ptr(), n, d, elld.data_ptr(), s0d.data_ptr(), nugd.data_ptr(),
+                          Dd.data_ptr(), q, F.data_ptr(), npad, st) == 0
+    A = torch.stack([torch.eye(npad, dtype=DT) for _ in range(q)])
+    for k in range(q):
+        Ck = O.Matern32(X, X, ell[k], s0[k], nug[k])
+        A[k, :n, :n] = torch.eye(n, dtype=DT) + D[k] * ((Ck * sr[None, :]) * sr[:, None])     # lcgp.py:616
+    low = torch.tril(torch.ones(npad, npad, dtype=torch.bool))
+    assert rel(F.cpu()[:, low], A[:, low]) < 1e-14
+    DL = torch.zeros((q, nb, 128, 128), dtype=DT, device=dev); DU = torch.zeros_like(DL)
+    ldp = torch.zeros((q, nb), dtype=DT, device=dev); info = torch.ones(q, dtype=torch.int32, device=dev)
+    assert L.lcgp_potrf_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), ldp.data_ptr(), info.data_ptr(), st) == 0
+    Lref = torch.linalg.cholesky(A)
+    assert info.cpu().tolist() == [0] * q
+    assert rel(F.cpu()[:, low], Lref[:, low]) < 1e-12
+    assert rel(ldp.sum(1), torch.log(torch.diagonal(Lref, dim1=1, dim2=2)).sum(1)) < 1e-12
+    sb = int(L.lcgp_trtri_scratch_bytes(npad, q))
+    scr = torch.empty(max(sb // 8, 1), dtype=DT, device=dev)
+    assert L.lcgp_trtri_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), scr.data_ptr(), sb, st) == 0
+    Uref = torch.linalg.solve_triangular(Lref, torch.eye(npad, dtype=DT).expand_as(Lref), upper=False).transpose(1, 2)
+    Fc = F.cpu()
+    for I in range(nb):
+        sl = slice(I * 128, (I + 1) * 128)
+        assert rel(DU[:, I], Uref[:, sl, sl]) < 1e-11 and rel(DL[:, I], Uref[:, sl, sl].transpose(1, 2)) < 1e-11
+        if I + 1 < nb:
+            assert rel(Fc[:, sl, (I + 1) * 128:], Uref[:, sl, (I + 1) * 128:]) < 1e-11
+
+
+def test_potrf_reports_bad_pivot():
+    L = _cabi.lib(); dev = torch.device('cuda')
+    F = torch.eye(256, dtype=DT, device=dev).repeat(2, 1, 1).contiguous()
+    F[1, 130, 130] = -1.0
+    DL = torch.zeros((2, 2, 128, 128), dtype=DT, device=dev); DU = torch.zeros_like(DL)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    assert L.lcgp_potrf_batched(F.data_ptr(), 256, 2, DL.data_ptr(), DU.data_ptr(), None, info.data_ptr(), _cabi.stream_ptr()) == 0
+    assert info.cpu().tolist() == [0, 131]
+    assert L.lcgp_potrf_batched(F.data_ptr(), 200, 2, DL.data_ptr(), DU.data_ptr(), None, info.data_ptr(), _cabi.stream_ptr()) == -2
+    assert L.lcgp_potrf_batched(None, 256, 2, DL.data_ptr(), DU.data_ptr(), None, info.data_ptr(), _cabi.stream_ptr()) == -1
+
+
+# ---------------------------------------------------------------- a2-a4: objective and gradient
+def _pair(x, y, **kw):
+    return LCGP(y=y, x=x, **kw), O.LCGPOracle(y=y, x=x, **kw)
+
+
+def _check_loss_grad(m, o, loss_fn=None):
+    f, g = m.loss_and_grad()
+    fo, go = o.loss_and_grad(loss_fn)
+    assert abs(f - fo) <= NLL_TOL * abs(fo), (f, fo)
+    assert np.max(np.abs(g - go)) <= GRAD_TOL * np.max(np.abs(go))
+    o1 = 0
+    for v in m.trainable_variables:          # per parameter block, so a small block cannot hide
+        k = v.numel()
+        den = np.max(np.abs(go[o1:o1 + k]))
+        assert np.max(np.abs(g[o1:o1 + k] - go[o1:o1 + k])) <= GRAD_TOL * max(den, 1e-3 * np.max(np.abs(go)))
+        o1 += k
+
+
+@pytest.mark.parametrize('case', ['rep1d_q3', 'rep1d_q2', 'rep3d', 'rep_ragged_groups', 'rep_nostd_nonrobust',
+                                  'rep_n129', 'rep_n700_d5', 'rep_q1'])
+def test_rep_objective_gradient(case):
+    if case.startswith('rep1d'):
+        x, y, _, _ = synthetic.rep1d_skewed(); kw = dict(q=int(case[-1]), submethod='rep')
+    elif case == 'rep3d':
+        x, y, _ = synthetic.rep3d(); kw = dict(q=3, submethod='rep')
+    elif case == 'rep_ragged_groups':
+        x, y, _ = make_ragged_rep_data(seed=2, n_unique=90, p=6, d=3); kw = dict(q=4, submethod='rep', diag_error_structure=[2, 1, 3])
+    elif case == 'rep_nostd_nonrobust':
+        x, y, _ = make_ragged_rep_data(seed=3, n_unique=60, p=4, d=2)
+        kw = dict(q=2, submethod='rep', rep_standardize_ybar=False, robust_mean=False)
+    elif case == 'rep_n129':
+        x, y, _ = make_ragged_rep_data(seed=4, n_unique=129, p=5, d=4); kw = dict(q=3, submethod='rep')
+    elif case == 'rep_n700_d5':
+        x, y, _ = make_ragged_rep_data(seed=5, n_unique=700, p=12, d=5); kw = dict(q=4, submethod='rep')
+    else:
+        x, y, _ = make_ragged_rep_data(seed=6, n_unique=50, p=3, d=1); kw = dict(q=1, submethod='rep')
+    m, o = _pair(x, y, **kw)
+    _check_loss_grad(m, o)                    # init_params point
+    move_params(m, o)
+    _check_loss_grad(m, o)                    # off-init point
+    assert float(m.neglpost_rep()) == pytest.approx(float(o.neglpost_rep().detach()), rel=NLL_TOL)
+
+
+@pytest.mark.parametrize('n,p,d,q', [(50, 4, 2, 4), (150, 6, 4, 3), (300, 5, 3, 2)])
+def test_full_objective_gradient(n, p, d, q):
+    x, y = make_full_data(seed=n, n=n, p=p, d=d)
+    m, o = _pair(x, y, q=q, submethod='full')
+    _check_loss_grad(m, o, o.neglpost_chol)
+    move_params(m, o)
+    _check_loss_grad(m, o, o.neglpost_chol)
+    # the literal eigh form (lcgp.py:650-664) agrees with the Cholesky form the kernels implement
+    assert abs(float(m.neglpost()) - float(o.neglpost().detach())) <= 1e-9 * abs(float(o.neglpost().detach()))
+
+
+def test_committed_fixtures():
+    """Known answers committed under tests/golden (independent of running the oracle on this box)."""
+    for case in FIX:
+        if case['name'].startswith('rep1d'):
+            x, y, xt, _ = synthetic.rep1d_skewed(); x0 = xt[::40]
+        elif case['name'] == 'rep3d':
+            x, y, x0 = synthetic.rep3d(); x0 = x0[:8]
+        else:
+            x, y, x0, _ = synthetic.latent_mixture(n=150, d=4, p=6, q_true=3, seed=5, rep_choices=None, n0=8)
+        m = LCGP(y=y, x=x, **case['model'])
+        f, g = m.loss_and_grad()
+        assert abs(f - case['init']['loss']) <= 1e-9 * abs(f)       # 'full' fixtures come from the eigh form
+        assert rel(g, case['init']['grad']) < 1e-7
+        mv = case['moved']
+        m.lLmb.assign(mv['lLmb']); m.lLmb0.assign(mv['lLmb0']); m.lsigma2s.assign(mv['lsigma2s']); m.lnugGPs.assign(mv['lnugGPs'])
+        f, g = m.loss_and_grad()
+        assert abs(f - mv['loss']) <= 1e-9 * abs(f) and rel(g, mv['grad']) < 1e-7
+        yp, ypv, ycv = m.predict(x0)
+        assert rel(yp, mv['ypred']) < PRED_TOL and rel(ypv, mv['ypredvar']) < PRED_TOL and rel(ycv, mv['yconfvar']) < PRED_TOL
+
+
+def test_gradient_matches_finite_differences():
+    x, y, _ = make_ragged_rep_data(seed=7, n_unique=200, p=5, d=3)
+    m = LCGP(y=y, x=x, q=3, submethod='rep')
+    f0, g = m.loss_and_grad()
+    v0 = m._flat_get()
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        dirn = rng.standard_normal(v0.size); dirn /= np.linalg.norm(dirn)
+        h = 1e-6
+        m._flat_set(v0 + h * dirn); fp = float(m.loss())
+        m._flat_set(v0 - h * dirn); fm = float(m.loss())
+        assert abs((fp - fm) / (2 * h) - g @ dirn) <= 2e-6 * max(1.0, abs(g @ dirn))
+
+
+# ---------------------------------------------------------------- a5-a8: aux quantities and prediction
+@pytest.mark.parametrize('sub', ['rep', 'full'])
+def test_predict_and_aux(sub):
+    if sub == 'rep':
+        x, y, xu = make_ragged_rep_data(seed=8, n_unique=140, p=5, d=3); xt = xu
+    else:
+        x, y = make_full_data(seed=8, n=140, p=5, d=3); xt = x
+    m, o = _pair(x, y, q=3, submethod=sub)
+    move_params(m, o)
+    x0 = np.random.default_rng(1).uniform(0, 1, (37, 3))
+    res, reso = m.predict(x0), o.predict(torch.as_tensor(x0))
+    for a, b in zip(res, reso):
+        assert a.shape == (5, 37) and rel(a, b) < PRED_TOL
+    assert rel(m.ghat, o.ghat) < PRED_TOL and rel(m.gvar, o.gvar) < PRED_TOL
+    assert rel(m.CinvMs, o.CinvMs) < PRED_TOL
+    if sub == 'rep':
+        assert rel(m.mks, o.mks) < PRED_TOL
+        assert rel(m.Tks[1], o.Tks[1]) < PRED_TOL            # oracle Tks in the stable form (helpers/oracle docstring)
+        assert rel(m.psi_c, o.psi_c) < 1e-12
+    else:
+        Th = m.Ths[0]
+        assert rel(Th @ Th.T, o.Ths[0] @ o.Ths[0].T) < PRED_TOL   # Th Th^T = (C + I/d)^-1, lcgp.py:709-715
+    # prediction AT the training inputs exercises the nugget-on-equal-inputs branch (covmat.py:46-53)
+    res, reso = m.predict(xt), o.predict(torch.as_tensor(xt))
+    for a, b in zip(res, reso):
+        assert rel(a, b) < PRED_TOL
+    # chunked prediction (n0 > chunk) gives the same answer
+    big = np.random.default_rng(2).uniform(0, 1, (300, 3))
+    g1, v1, _ = m._predict_latents(torch.as_tensor(big), m.x_unique_s if sub == 'rep' else m.x, chunk=128)
+    g2, v2, _ = m._predict_latents(torch.as_tensor(big), m.x_unique_s if sub == 'rep' else m.x, chunk=4096)
+    assert torch.equal(g1, g2) and torch.equal(v1, v2)
+
+
+def test_fullcov_and_rep_fullcov_none():       # test_coverage_gaps.py:169-232
+    x, y = make_full_data(seed=0, n=40, p=3, d=2)
+    m, o = _pair(x, y, submethod='full')
+    x0 = np.random.default_rng(11).uniform(0, 1, (8, 2))
+    yp, ypv, ycv, full = m.predict(x0, return_fullcov=True)
+    assert full.shape == (8, 3, 3)
+    np.testing.assert_allclose(np.diagonal(full.numpy(), axis1=1, axis2=2).T, ypv.numpy(), rtol=1e-5, atol=1e-6)
+    assert rel(full, o.predict(torch.as_tensor(x0), return_fullcov=True)[3]) < PRED_TOL
+    xr, yr, _ = make_rep_data(n_unique=20, p=4, d=2, reps=3)
+    mr = LCGP(y=yr, x=xr, submethod='rep', rep_standardize_ybar=False)
+    out = mr.predict(x0, return_fullcov=True)
+    assert len(out) == 4 and out[3] is None and torch.isfinite(out[0]).all()
+
+
+# ---------------------------------------------------------------- a10: fit
+@pytest.mark.parametrize('optimizer', ['L-BFGS-B', 'torch-lbfgs'])
+def test_fit_matches_oracle_under_shared_optimizer(optimizer):
+    """Oracle and CUDA path under ONE optimizer, start and tolerance setting (SURVEY 7 'hard parts')."""
+    x, y, xu = make_ragged_rep_data(seed=9, n_unique=80, p=4, d=2)
+    m, o = _pair(x, y, q=3, submethod='rep')
+    l0 = float(m.loss())
+    if optimizer == 'L-BFGS-B':
+        m.fit(optimizer=optimizer, maxiter=60, ftol=1e-14, gtol=1e-9)
+        o.fit(method='L-BFGS-B', maxiter=60, ftol=1e-14, gtol=1e-9)
+    else:
+        m.fit(optimizer=optimizer, max_iter=40)
+        o.fit(method='torch-lbfgs', max_iter=40)
+    l1, lo1 = float(m.loss()), float(o.loss().detach())
+    assert l1 <= l0 + 1e-3                                       # test_rep.py:161-171
+    assert abs(l1 - lo1) <= 1e-8 * abs(lo1)
+    x0 = np.random.default_rng(5).uniform(0, 1, (25, 2))
+    for a, b in zip(m.predict(x0), o.predict(torch.as_tensor(x0))):
+        assert rel(a, b) < 1e-5
+    # identifiable blocks agree tightly; lLmb0 / nugget sit on a flat ridge (SURVEY B-16) -> looser
+    assert rel(m.lLmb.numpy(), o.lLmb.detach().numpy()) < 1e-4
+    assert rel(m.lsigma2s.numpy(), o.lsigma2s.detach().numpy()) < 1e-4
+    for t in m.get_param():
+        assert torch.isfinite(t).all()
+
+
+def test_notebook_goldens_through_cuda_path():
+    """End to end on the notebook case: the reference's stored metrics, produced by the CUDA path."""
+    xtr, ytr, xte, ytrue = synthetic.rep1d_skewed()
+    m = LCGP(y=ytr, x=xtr, q=3, submethod='rep', diag_error_structure=[1, 1, 1], robust_mean=True)
+    np.testing.assert_allclose(m.diag_D.numpy(), GOLD['diag_D'], atol=5e-9)
+    assert abs(float(m.loss()) - 0.2793219611474477) < 1e-11
+    m.fit()
+    np.testing.assert_allclose(m.lLmb.numpy().ravel(), GOLD['fitted_lengthscales'], rtol=1e-3)
+    np.testing.assert_allclose(m.lsigma2s.numpy(), GOLD['fitted_lsigma2s'], rtol=1e-3)
+    yp, ypv, ycv = (t.numpy() for t in m.predict(xte))
+    assert round(float(evaluation.rmse(ytrue, yp)), 4) == GOLD['rmse']
+    assert round(float(evaluation.normalized_rmse(ytrue, yp)), 4) == GOLD['nrmse']
+    cov, width = evaluation.intervalstats(ytrue, yp, ycv)
+    assert round(float(cov), 3) == GOLD['coverage'] and round(float(width), 4) == GOLD['width']
+    assert abs(evaluation.dss(ytrue, yp, ycv, use_diag=True) - GOLD['dss']) < 2e-4
+    assert np.all(ypv > 0) and np.all(ycv <= ypv + 1e-9)         # test_rep.py:203-232
+
+
+def test_reference_behaviour_contract():
+    """Shape / invariants the reference tests assert after fit+predict (test_training.py, test_rep.py)."""
+    x, y = make_full_data(seed=1, n=50, p=4, d=2)
+    m = LCGP(y=y, x=x, submethod='full')
+    m.fit()
+    yp, ypv, ycv = m.predict(x0=x)                              # at the training inputs, test_training.py:15
+    assert yp.shape == (4, 50) and torch.isfinite(yp).all() and (ypv > 0).all() and (ycv <= ypv + 1e-9).all()
+    assert len(m.get_param()) == 4
+    xr, yr, xu = make_rep_data(seed=0, n_unique=20, p=4, d=2, reps=3)
+    mr = LCGP(y=yr, x=xr, submethod='rep')
+    mr.submethod = 'bogus'
+    with pytest.raises(KeyError):
+        mr.predict(x0=mr.x_unique)                              # test_coverage_gaps.py:138-147
+    with pytest.raises(ValueError):
+        mr.loss()
+    mr.submethod = 'rep'
+    mr.CinvMs = torch.full((mr.q, int(mr.n)), float('nan'), dtype=DT); mr.Tks = None
+    mr.compute_aux_predictive_quantities()                      # test_coverage_gaps.py:149-166
+    assert mr.Tks is not None and not torch.isnan(mr.CinvMs).any()
+    mr.fit()                                                    # a second predict after fit must not reuse stale aux
+    a = mr.predict(xu)[0]
+    mr.lLmb.assign(mr.lLmb.numpy() * 1.3)
+    assert rel(mr.predict(xu)[0], a) > 1e-6
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+def test_properties_at_config3_scale():
+    """n=2000, d=8 (BASELINE config 3 shape, fewer latents): properties that need no CPU oracle run --
+    L L^T = A, U L^T = I on block rows, gradient vs central differences, predvar bounds."""
+    L = _cabi.lib(); dev = torch.device('cuda')
+    n, d, q = 2000, 8, 2
+    rng = np.random.default_rng(2000)
+    X = torch.as_tensor(rng.uniform(0, 1, (n, d)), device=dev); sr = torch.sqrt(torch.as_tensor(rng.integers(1, 5, n).astype(float), device=dev))
+    ell = torch.full((q, d), 0.8, dtype=DT, device=dev); s0 = torch.ones(q, dtype=DT, device=dev)
+    nug = torch.full((q,), float(np.exp(-10.0)), dtype=DT, device=dev); D = torch.tensor([0.5, 2.0], dtype=DT, device=dev)
+    npad = _cabi.padded(n); nb = npad // 128; st = _cabi.stream_ptr()
+    F = torch.empty((q, npad, npad), dtype=DT, device=dev)
+    L.lcgp_build_A(X.data_ptr(), sr.data_ptr(), n, d, ell.data_ptr(), s0.data_ptr(), nug.data_ptr(), D.data_ptr(), q, F.data_ptr(), npad, st)
+    A = torch.tril(F) + torch.tril(F, -1).transpose(1, 2)
+    DL = torch.zeros((q, nb, 128, 128), dtype=DT, device=dev); DU = torch.zeros_like(DL)
+    info = torch.zeros(q, dtype=torch.int32, device=dev)
+    L.lcgp_potrf_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), None, info.data_ptr(), st)
+    Lf = torch.tril(F)
+    resid = (Lf @ Lf.transpose(1, 2) - A).abs().max() / A.abs().max()
+    assert float(resid) < 1e-13 and info.cpu().tolist() == [0, 0]
+    sb = int(L.lcgp_trtri_scratch_bytes(npad, q)); scr = torch.empty(sb // 8, dtype=DT, device=dev)
+    L.lcgp_trtri_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), scr.data_ptr(), sb, st)
+    U = torch.triu(F, 1)
+    for I in range(nb):
+        U[:, I * 128:(I + 1) * 128, I * 128:(I + 1) * 128] = DU[:, I]
+    eye = torch.eye(npad, dtype=DT, device=dev)
+    assert float((U @ Lf.transpose(1, 2) - eye).abs().max()) < 1e-10          # U = L^-T
+    # model-level: gradient vs central differences and variance bounds at n = 2000
+    x, y, x0, _, mk = synthetic.make_config('cfg3_rep', p=40)
+    m = LCGP(y=y, x=x, q=3, submethod='rep')
+    f0, g = m.loss_and_grad()
+    v0 = m._flat_get()
+    dirn = np.random.default_rng(1).standard_normal(v0.size); dirn /= np.linalg.norm(dirn)
+    h = 1e-5
+    m._flat_set(v0 + h * dirn); fp = float(m.loss())
+    m._flat_set(v0 - h * dirn); fm = float(m.loss())
+    m._flat_set(v0)
+    assert abs((fp - fm) / (2 * h) - g @ dirn) <= 1e-5 * max(1.0, abs(g @ dirn))
+    yp, ypv, ycv = m.predict(x0)
+    assert torch.isfinite(yp).all() and (ypv > 0).all() and (ycv <= ypv + 1e-9).all() and (ycv > -1e-9).all()
