@@ -4,7 +4,80 @@
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
 
+#include <cstdlib>
+#include <mutex>
+
 namespace lcgp {
+
+// ---- tunables (environment, read once) --------------------------------------------------------
+//   LCGP_PANEL_W  : block columns per Cholesky panel (K = 128 * W in the trailing update); default 8
+//   LCGP_STREAMS  : independent groups of latents factored on separate streams so that one group's
+//                   serial panel work overlaps another group's trailing updates; default min(4, q_loc)
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    int v = std::atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+static int panel_width() { static const int v = env_int("LCGP_PANEL_W", 8, 1, 16); return v; }
+constexpr int MAX_GROUPS = 4;
+static int stream_groups(int q) {
+    static const int v = env_int("LCGP_STREAMS", MAX_GROUPS, 1, MAX_GROUPS);
+    return q < v ? q : v;
+}
+
+// Side streams + fork/join events, created on first use for the current device.  The library
+// still allocates no device memory; these are the only objects that outlive a call.
+struct SidePool {
+    int device = -1;
+    cudaStream_t s[MAX_GROUPS];
+    cudaEvent_t fork, join[MAX_GROUPS];
+    std::mutex mu;
+    cudaError_t ensure() {
+        int dev;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev == device) return cudaSuccess;
+        for (int i = 0; i < MAX_GROUPS; ++i) {
+            if ((e = cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        device = dev;
+        return cudaSuccess;
+    }
+};
+static SidePool& side_pool() { static SidePool p; return p; }
+
+// Runs f(first_latent, count, stream) for G contiguous groups of the q latents, each on its own
+// side stream, between a fork from and a join back into `main`.
+template <class F>
+static cudaError_t run_grouped(cudaStream_t main, int q, int G, F f) {
+    if (G <= 1) return f(0, q, main);
+    SidePool& P = side_pool();
+    std::lock_guard<std::mutex> lock(P.mu);
+    cudaError_t e = P.ensure();
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(P.fork, main)) != cudaSuccess) return e;
+    int g0 = 0;
+    for (int g = 0; g < G; ++g) {
+        const int cnt = q / G + (g < q % G ? 1 : 0);
+        if ((e = cudaStreamWaitEvent(P.s[g], P.fork, 0)) != cudaSuccess) return e;
+        if ((e = f(g0, cnt, P.s[g])) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(P.join[g], P.s[g])) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(main, P.join[g], 0)) != cudaSuccess) return e;
+        g0 += cnt;
+    }
+    return cudaSuccess;
+}
+
+static FactorView sub_view(const FactorView& v, int g0) {
+    FactorView s = v;
+    s.F = v.F + (size_t)g0 * v.fstride;
+    s.DL = v.DL + (size_t)g0 * v.dstride;
+    s.DU = v.DU + (size_t)g0 * v.dstride;
+    return s;
+}
 
 constexpr int JSPLIT = 8;  // split of the p-reduction in the B = V^T YR product
 
@@ -212,9 +285,15 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     // A_k
     LCGP_CUDA(launch_build_A(P->X, P->sr, n, d, w.np, kp, w.F, w.fstride, q, st));
     rec(1);
-    LCGP_CUDA(potrf_batched(v, w.DL, w.DU, q, w.logdet_part, info, st));
+    const int G = stream_groups(q);
+    LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
+        return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
+                             w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s);
+    }));
     rec(2);
-    LCGP_CUDA(trtri_batched(v, w.T, w.tstride, q, st));
+    LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
+        return trtri_batched(sub_view(v, g0), w.T + (size_t)g0 * w.tstride, w.tstride, cnt, s);
+    }));
     rec(3);
     SolveArgs a;
     a.n = n; a.d = d; a.p = p; a.np = w.np; a.nb = w.nb; a.q_loc = q;
@@ -389,7 +468,7 @@ int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double*
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
-    return cuda_rc(potrf_batched(v, DL, DU, batch, logdet_part, info, st));
+    return cuda_rc(potrf_batched(v, DL, DU, batch, logdet_part, info, panel_width(), st));
 }
 
 size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch) {

@@ -9,10 +9,10 @@ namespace lcgp {
 // identity so that L, L^{-1} and A^{-1} are the identity there and never mix with real rows.
 constexpr int NB = 128;          // Cholesky / TRTRI block and GEMM CTA tile edge
 constexpr int GEMM_THREADS = 256;
-constexpr int BK = 16;           // K extent of one pipeline stage (doubles) = 128 B per tile row
+constexpr int BK = 32;           // K extent of one pipeline stage (doubles) = 256 B per tile row
 constexpr int KSTEPS = NB / BK;  // pipeline iterations per NB-wide K block
-constexpr int STAGES = 4;
-constexpr int LDS_K = BK + 4;    // smem pitch of a K-major tile row (20: conflict-free LDS.64 fragments)
+constexpr int STAGES = 3;
+constexpr int LDS_K = BK + 4;    // smem pitch of a K-major tile row (36 = 4 mod 16: conflict-free LDS.64 fragments)
 constexpr int LDS_N = NB + 4;    // smem pitch of an N-major tile row (132)
 constexpr int A_STAGE = NB * LDS_K;              // doubles per stage, K-major operand
 constexpr int BN_STAGE = BK * LDS_N;             // doubles per stage, N-major operand
@@ -22,9 +22,10 @@ constexpr size_t GEMM_SMEM_NMAJOR = sizeof(double) * STAGES * (A_STAGE + BN_STAG
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---- cp.async (LDGSTS) -------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+// dst is a 32-bit shared-window address (computed once per kernel with __cvta_generic_to_shared, so
+// the generic->shared conversion -- an S2R of the CTA id -- stays out of the pipelined loop)
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>

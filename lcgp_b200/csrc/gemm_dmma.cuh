@@ -3,7 +3,7 @@
 // One CTA (8 warps, warp tile 64x32, 64 accumulator doubles per thread) produces one 128x128
 // tile  acc[m][n] = sum_k A[m][k] * B[n][k].  Operand A is always K-major (row m contiguous in
 // k); operand B is K-major or N-major (B[k][n], row k contiguous in n).  Tiles are staged through
-// a 4-deep cp.async ring in shared memory with padded pitches chosen so that every DMMA fragment
+// a 3-deep cp.async ring (32-deep K stages) in shared memory with padded pitches chosen so that every DMMA fragment
 // load (LDS.64) is bank-conflict free.  The K range is a run of NB-wide blocks [kb0, kb1); a Job
 // supplies the tile base pointer per K block (so triangular operands can switch between the big
 // factor buffer and the dense diagonal-block arrays) and an epilogue that consumes the register
@@ -28,7 +28,7 @@ struct WarpCoord {
 
 template <class Job>
 __device__ __forceinline__ void gemm_load_stage(const typename Job::Params& p, const Job& job, int it,
-                                                double* As, double* Bs) {
+                                                unsigned As, unsigned Bs) {
     const int kb = job.kb0 + it / KSTEPS;
     const int ks = it % KSTEPS;
     const double* pa;
@@ -37,34 +37,36 @@ __device__ __forceinline__ void gemm_load_stage(const typename Job::Params& p, c
     job.a_src(p, kb, pa, lda);
     job.b_src(p, kb, pb, ldb);
     const int tid = threadIdx.x;
+    constexpr int CPR = BK / 2;                       // 16-byte chunks per K-major tile row
+    constexpr int NCH = NB * CPR / GEMM_THREADS;      // chunks per thread per operand
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NCH; ++u) {
         const int c = tid + u * GEMM_THREADS;
-        const int row = c >> 3, kc = c & 7;
-        cp_async16(As + row * LDS_K + kc * 2, pa + (size_t)row * lda + ks * BK + kc * 2);
+        const int row = c / CPR, kc = c % CPR;
+        cp_async16(As + (row * LDS_K + kc * 2) * 8, pa + (size_t)row * lda + ks * BK + kc * 2);
     }
     if (!Job::kBNMajor) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCH; ++u) {
             const int c = tid + u * GEMM_THREADS;
-            const int row = c >> 3, kc = c & 7;
-            cp_async16(Bs + row * LDS_K + kc * 2, pb + (size_t)row * ldb + ks * BK + kc * 2);
+            const int row = c / CPR, kc = c % CPR;
+            cp_async16(Bs + (row * LDS_K + kc * 2) * 8, pb + (size_t)row * ldb + ks * BK + kc * 2);
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCH; ++u) {
             const int c = tid + u * GEMM_THREADS;
-            const int krow = c >> 6, nc = c & 63;
-            cp_async16(Bs + krow * LDS_N + nc * 2, pb + (size_t)(ks * BK + krow) * ldb + nc * 2);
+            const int krow = c >> 6, nc = c & 63;     // 64 chunks per 128-wide N-major row
+            cp_async16(Bs + (krow * LDS_N + nc * 2) * 8, pb + (size_t)(ks * BK + krow) * ldb + nc * 2);
         }
     }
 }
 
-template <bool BNMAJOR>
+template <bool BNMAJOR, int KK0, int KK1>
 __device__ __forceinline__ void gemm_compute_stage(const double* __restrict__ As, const double* __restrict__ Bs,
                                                    double (&acc)[8][4][2], const WarpCoord& wc) {
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
+    for (int kk = KK0; kk < KK1; ++kk) {
         double a[8], b[4];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) a[mi] = As[(wc.wm * 64 + mi * 8 + wc.g) * LDS_K + kk * 4 + wc.t];
@@ -81,12 +83,18 @@ __device__ __forceinline__ void gemm_compute_stage(const double* __restrict__ As
 
 // Runs the pipelined K loop of `job` and leaves the tile in `acc`.  On return all cp.async
 // groups have drained and all threads have passed a barrier, so `smem` may be reused.
+// One barrier per BK-deep stage; the loads for stage it+STAGES-1 (which overwrite the buffer
+// consumed in iteration it-1, free since the barrier) are issued after the first quarter of the
+// stage's MMAs so that the tensor pipe already has work queued while the LSU issues them.
 template <class Job>
 __device__ __forceinline__ void gemm_mainloop(const typename Job::Params& p, const Job& job,
                                               double (&acc)[8][4][2], double* smem, const WarpCoord& wc) {
     constexpr int B_STAGE = Job::kBNMajor ? BN_STAGE : A_STAGE;
+    constexpr int KK = BK / 4;
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
+    const unsigned As_u = (unsigned)__cvta_generic_to_shared(As);
+    const unsigned Bs_u = (unsigned)__cvta_generic_to_shared(Bs);
     const int niter = (job.kb1 - job.kb0) * KSTEPS;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -95,20 +103,20 @@ __device__ __forceinline__ void gemm_mainloop(const typename Job::Params& p, con
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < niter) gemm_load_stage<Job>(p, job, s, As + s * A_STAGE, Bs + s * B_STAGE);
+        if (s < niter) gemm_load_stage<Job>(p, job, s, As_u + s * A_STAGE * 8, Bs_u + s * B_STAGE * 8);
         cp_async_commit();
     }
+    int cur = 0, nst = STAGES - 1;
     for (int it = 0; it < niter; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+        gemm_compute_stage<Job::kBNMajor, 0, KK / 4>(As + cur * A_STAGE, Bs + cur * B_STAGE, acc, wc);
         const int nxt = it + STAGES - 1;
-        if (nxt < niter) {
-            const int st = nxt % STAGES;
-            gemm_load_stage<Job>(p, job, nxt, As + st * A_STAGE, Bs + st * B_STAGE);
-        }
+        if (nxt < niter) gemm_load_stage<Job>(p, job, nxt, As_u + nst * A_STAGE * 8, Bs_u + nst * B_STAGE * 8);
         cp_async_commit();
-        const int cur = it % STAGES;
-        gemm_compute_stage<Job::kBNMajor>(As + cur * A_STAGE, Bs + cur * B_STAGE, acc, wc);
+        gemm_compute_stage<Job::kBNMajor, KK / 4, KK>(As + cur * A_STAGE, Bs + cur * B_STAGE, acc, wc);
+        cur = (cur + 1 == STAGES) ? 0 : cur + 1;
+        nst = (nst + 1 == STAGES) ? 0 : nst + 1;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -152,21 +160,29 @@ struct FactorView {
     size_t fstride, dstride;
 };
 
-// ---- Cholesky trailing update:  C[I][J] -= P_I P_J^T  for jb < J <= I ----------------------
+// ---- Cholesky updates:  C[I][J] -= sum_{kb in [kb0,kb1)} P_I,kb P_J,kb^T ------------------------
+//   col <  0 : trailing update, all tiles jstart <= J <= I < nb (lower triangle of the trailing matrix)
+//   col >= 0 : left-looking update of block column `col` inside a panel: tiles (I, col), I >= col
 struct SyrkJob {
     static constexpr bool kBNMajor = false;
-    struct Params { FactorView v; int jb; };
+    struct Params { FactorView v; int kb0, kb1, jstart, col; };
     int kb0, kb1, I, J;
     double* base;
     __device__ bool init(const Params& p) {
-        const int T = p.v.nb - p.jb - 1;
-        if ((int)blockIdx.x >= T * (T + 1) / 2) return false;
-        int ti, tj;
-        tri_decode(blockIdx.x, ti, tj);
-        I = p.jb + 1 + ti;
-        J = p.jb + 1 + tj;
-        kb0 = p.jb;
-        kb1 = p.jb + 1;
+        if (p.col >= 0) {
+            I = p.col + blockIdx.x;
+            J = p.col;
+            if (I >= p.v.nb) return false;
+        } else {
+            const int T = p.v.nb - p.jstart;
+            if ((int)blockIdx.x >= T * (T + 1) / 2) return false;
+            int ti, tj;
+            tri_decode(blockIdx.x, ti, tj);
+            I = p.jstart + ti;
+            J = p.jstart + tj;
+        }
+        kb0 = p.kb0;
+        kb1 = p.kb1;
         base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
         return true;
     }

@@ -10,7 +10,7 @@ struct FactorView;
 
 // potrf.cu
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, cudaStream_t stream);
+                          int* info, int panel_width, cudaStream_t stream);
 size_t trtri_scratch_blocks(int nb);
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);
 

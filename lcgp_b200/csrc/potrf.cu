@@ -2,7 +2,7 @@
 //
 //   per block column jb:   diag kernel  : L_jj = chol(A_jj), DL = inv(L_jj), DU = DL^T, logdet part
 //                          TrsmJob      : P = A[jb+1:, jb] * DL^T                 (DMMA GEMM)
-//                          SyrkJob      : A[I][J] -= P_I P_J^T, jb < J <= I       (DMMA GEMM)
+//                          SyrkJob      : A[I][J] -= P_I P_J^T (panel-column and trailing updates, DMMA GEMM)
 //   TRTRI: bottom-up binary merges of already-inverted diagonal ranges, two DMMA GEMMs per level.
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
@@ -126,22 +126,40 @@ static cudaError_t diag_configure() {
     return e;
 }
 
+// Two-level blocking: panels of `pw` block columns are factored left-looking (block column j is
+// first updated with the panel's earlier columns, K = 128 (j - j0), then its diagonal block is
+// factored and the rows below solved); the matrix to the right of the panel then gets ONE trailing
+// update with K = 128 pw, which halves / quarters the C read-modify-write traffic and the number of
+// pipeline fills per flop compared with a rank-128 update per block column.
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, cudaStream_t stream) {
+                          int* info, int pw, cudaStream_t stream) {
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
-    for (int jb = 0; jb < v.nb; ++jb) {
-        potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, stream>>>(v, DLw, DUw, jb, logdet_part, info);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        const int T = v.nb - jb - 1;
-        if (T == 0) break;
-        TrsmJob::Params tp{v, jb};
-        e = gemm_launch<TrsmJob>(tp, dim3(T, batch, 1), stream);
-        if (e != cudaSuccess) return e;
-        SyrkJob::Params sp{v, jb};
-        e = gemm_launch<SyrkJob>(sp, dim3(T * (T + 1) / 2, batch, 1), stream);
-        if (e != cudaSuccess) return e;
+    if (pw < 1) pw = 1;
+    for (int j0 = 0; j0 < v.nb; j0 += pw) {
+        const int j1 = (j0 + pw < v.nb) ? j0 + pw : v.nb;
+        for (int j = j0; j < j1; ++j) {
+            if (j > j0) {
+                SyrkJob::Params cp{v, j0, j, 0, j};
+                e = gemm_launch<SyrkJob>(cp, dim3(v.nb - j, batch, 1), stream);
+                if (e != cudaSuccess) return e;
+            }
+            potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, stream>>>(v, DLw, DUw, j, logdet_part, info);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            const int T = v.nb - j - 1;
+            if (T > 0) {
+                TrsmJob::Params tp{v, j};
+                e = gemm_launch<TrsmJob>(tp, dim3(T, batch, 1), stream);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        const int T = v.nb - j1;
+        if (T > 0) {
+            SyrkJob::Params sp{v, j0, j1, j1, -1};
+            e = gemm_launch<SyrkJob>(sp, dim3(T * (T + 1) / 2, batch, 1), stream);
+            if (e != cudaSuccess) return e;
+        }
     }
     return cudaSuccess;
 }

@@ -109,14 +109,23 @@ class CudaEngine:
         self._scratch = None
 
     def _count_launches(self):
+        """Kernel launches of one objective+gradient evaluation (mirrors csrc/api.cu / potrf.cu)."""
+        import os
         nb = _cabi.padded(self.n) // _cabi.NB
-        levels = 0
-        s = 1
+        pw = min(max(int(os.environ.get('LCGP_PANEL_W', '8') or 8), 1), 16)
+        groups = min(self.q_loc, min(max(int(os.environ.get('LCGP_STREAMS', '4') or 4), 1), 4))
+        potrf = 0
+        for j0 in range(0, nb, pw):
+            j1 = min(j0 + pw, nb)
+            for j in range(j0, j1):
+                potrf += (1 if j > j0 else 0) + 1 + (1 if nb - j - 1 > 0 else 0)
+            potrf += 1 if nb - j1 > 0 else 0
+        levels, s = 0, 1
         while s < nb:
             levels += 1
             s *= 2
-        # prep(3) + build(1) + potrf(nb diag + (nb-1)*(trsm+syrk)) + trtri(2/level) + solve(4) + contract(2) + zmat + finalize
-        return 3 + 1 + nb + 2 * (nb - 1) + 2 * levels + 4 + 2 + 1 + 1
+        # prep(3) + build(1) + groups*(potrf + trtri 2/level) + solve(4) + contract(2) + zmat + finalize
+        return 3 + 1 + groups * (potrf + 2 * levels) + 4 + 2 + 1 + 1
 
     def _stage(self, lLmb, lLmb0, lnug, lsig_p):
         q, dd = self.q_loc, self.d

@@ -127,6 +127,9 @@ CONFIGS = {
                      model=dict(q=10, submethod='rep')),
     'cfg4_rep': dict(data=dict(n=8000, d=10, p=2000, q_true=32, seed=8000, rep_choices=(1, 2, 3)),
                      model=dict(q=32, submethod='rep')),
+    # per-GPU share of config 4 at N = 8 (4 of the 32 latents), for single-GPU tuning of the sharded case
+    'cfg4_shard8': dict(data=dict(n=8000, d=10, p=2000, q_true=32, seed=8000, rep_choices=(1, 2, 3)),
+                        model=dict(q=4, submethod='rep')),
     'cfg5_one': dict(data=dict(n=1024, d=6, p=64, q_true=8, seed=1024, rep_choices=None),
                      model=dict(q=8, submethod='full')),
 }
