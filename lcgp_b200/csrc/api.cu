@@ -286,15 +286,28 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     LCGP_CUDA(launch_build_A(P->X, P->sr, n, d, w.np, kp, w.F, w.fstride, q, st));
     rec(1);
     const int G = stream_groups(q);
-    LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
+    auto potrf_group = [&](int g0, int cnt, cudaStream_t s) {
         return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
                              w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s);
-    }));
-    rec(2);
-    LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
+    };
+    auto trtri_group = [&](int g0, int cnt, cudaStream_t s) {
         return trtri_batched(sub_view(v, g0), w.T + (size_t)g0 * w.tstride, w.tstride, cnt, s);
-    }));
-    rec(3);
+    };
+    if (ev) {
+        // stage timing requested: join the groups between Cholesky and triangular inverse so that the
+        // two stages can be timed separately
+        LCGP_CUDA(run_grouped(st, q, G, potrf_group));
+        rec(2);
+        LCGP_CUDA(run_grouped(st, q, G, trtri_group));
+        rec(3);
+    } else {
+        // production path: each group flows from its Cholesky straight into its triangular inverse, so
+        // one group's serial panel work and launch tails overlap another group's GEMMs
+        LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
+            cudaError_t e = potrf_group(g0, cnt, s);
+            return e != cudaSuccess ? e : trtri_group(g0, cnt, s);
+        }));
+    }
     SolveArgs a;
     a.n = n; a.d = d; a.p = p; a.np = w.np; a.nb = w.nb; a.q_loc = q;
     a.X = P->X; a.sr = P->sr; a.B = w.B; a.kp = kp;
