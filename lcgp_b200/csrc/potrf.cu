@@ -13,18 +13,21 @@ namespace lcgp {
 // Diagonal-block kernel: one CTA (16 x 16 threads) per matrix; the 128 x 128 block is REGISTER
 // resident, thread (ty, tx) owning S[ty + 16 i][tx + 16 j], i, j < 8.  The lower triangle is the
 // running Schur complement, the strictly-upper triangle the transpose of the running inverse Z of
-// the factor (Z[i][j] at S[j][i]).  Column step c: the 16 owners of column c publish it (u, with
-// u[c] := 1) and the pivot to shared memory, ONE barrier, then every thread applies
+// the factor (Z[i][j] at S[j][i]).  Column step c applies, with u = column c (u[c] := 1),
 //     S[a][b] -= u[a] u[b] / piv     for  b > c  and  (a >= b  or  a <= c)
 // which is at once the Cholesky trailing update and the forward elimination of the identity.
-// Column c is dead afterwards, so its scaling by 1/sqrt(piv_c) is deferred to the write-back
-// (L[a][c] = u[a]/sqrt(piv_c), Z[c][a] likewise).  u / piv are double-buffered by the parity of c,
-// which is what makes a single barrier per column sufficient.  The loop over the 16-column groups
-// is unrolled so that every ownership test on (i, j) folds at compile time.
+// Column c is dead afterwards, so its scaling by 1/sqrt(piv_c) is deferred to the write-back.
+//
+// Synchronisation is split-phase (mbarriers, no CTA-wide rendezvous in the loop): the 16 owners of
+// column c+1 update that column FIRST, publish it to shared memory and arrive on ready[(c+1)&1];
+// everybody then finishes the rest of step c while the publication propagates, and waits on the
+// mbarrier only at the top of step c+1.  consumed[] (256 arrivals, made as soon as a thread has the
+// column in registers) protects the two-deep u buffer against overwriting.  The critical path per
+// column is  wait -> LDS -> reciprocal -> 8 FMAs -> STS -> arrive  on 16 threads.
 // ------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
 constexpr int DPITCH = NB + 1;
-constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 2 * NB + NB + NB + 8);
+constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 2 * NB + NB + NB + 16);
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet_part /* [batch][nb] */,
@@ -34,12 +37,18 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
     double* ucol = sm + NB * DPITCH;    // [2][NB]
     double* pivs = ucol + 2 * NB;       // pivots of all columns
     double* invd = pivs + NB;           // 1 / L_cc
-    double* red = invd + NB;
+    double* red = invd + NB;            // 8 doubles of reduction scratch, then 4 mbarriers
+    const unsigned ready0 = smem_u32(red + 8);      // ready[2]
+    const unsigned cons0 = ready0 + 16;             // consumed[2]
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int bz = blockIdx.x;
     double* blk = v.F + (size_t)bz * v.fstride + (size_t)jb * NB * v.np + (size_t)jb * NB;
 
+    if (tid == 0) {
+        mbar_init(ready0, 16); mbar_init(ready0 + 8, 16);
+        mbar_init(cons0, DIAG_THREADS); mbar_init(cons0 + 8, DIAG_THREADS);
+    }
     double reg[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -49,45 +58,80 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
             reg[i][j] = (a >= b) ? blk[(size_t)a * v.np + b] : 0.0;
         }
     const bool p_low = ty >= tx;
+    __syncthreads();   // barriers initialised
+    if (tx == 0) {     // publish column 0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int a = ty + 16 * i;
+            if (i == 0 && ty == 0) { pivs[0] = reg[0][0]; ucol[a] = 1.0; }
+            else ucol[a] = reg[i][0];
+        }
+        mbar_arrive(ready0);
+    }
 
 #pragma unroll
     for (int jc = 0; jc < 8; ++jc) {
         for (int cc = 0; cc < 16; ++cc) {
             const int c = jc * 16 + cc;
-            double* ub_ = ucol + (c & 1) * NB;
-            if (tx == cc) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int a = ty + 16 * i;
-                    if (i == jc && ty == cc) { pivs[c] = reg[i][jc]; ub_[a] = 1.0; }
-                    else ub_[a] = reg[i][jc];
-                }
-            }
-            __syncthreads();
-            const double piv = pivs[c];
-            const double ipiv = 1.0 / piv;
+            const int buf = c & 1, use = c >> 1;
+            mbar_wait(ready0 + 8 * buf, use & 1);
+            const double* ub_ = ucol + buf * NB;
+            const double ipiv = fast_rcp(pivs[c]);
             double ua[8], ub[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ua[i] = ub_[ty + 16 * i] * ipiv;
+            for (int i = 0; i < 8; ++i) ua[i] = ub_[ty + 16 * i];
 #pragma unroll
             for (int j = 0; j < 8; ++j) ub[j] = ub_[tx + 16 * j];
+            mbar_arrive(cons0 + 8 * buf);    // this thread no longer needs the buffer
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ua[i] *= ipiv;
             const bool p_bgt = tx > cc, p_ale = ty <= cc;
+            // which register column holds global column c+1 for its owners (tx == (cc+1) & 15)
+            const bool own_next = (c + 1 < NB) && (tx == ((cc + 1) & 15));
+            // ---- phase 1: the column group(s) that can contain column c+1: j == jc and j == jc+1
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int j = jc; j < 8 && j <= jc + 1; ++j)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int i = 0; i < 8; ++i) {
                     const bool lower = (i > j) || (i == j && p_low);
                     const bool b_gt = (j > jc) || (j == jc && p_bgt);
                     const bool a_le = (i < jc) || (i == jc && p_ale);
                     if (b_gt && (lower || a_le)) reg[i][j] -= ua[i] * ub[j];
                 }
+            if (own_next) {
+                const int cn = c + 1, nbuf = cn & 1, nuse = cn >> 1;
+                mbar_wait(cons0 + 8 * nbuf, (nuse & 1) ^ 1);     // everyone has read the previous tenant
+                double* un = ucol + nbuf * NB;
+                if (cc < 15) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int a = ty + 16 * i;
+                        if (i == jc && ty == cc + 1) { pivs[cn] = reg[i][jc]; un[a] = 1.0; }
+                        else un[a] = reg[i][jc];
+                    }
+                } else if (jc < 7) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int a = ty + 16 * i;
+                        if (i == jc + 1 && ty == 0) { pivs[cn] = reg[i][(jc + 1) & 7]; un[a] = 1.0; }
+                        else un[a] = reg[i][(jc + 1) & 7];
+                    }
+                }
+                mbar_arrive(ready0 + 8 * nbuf);
+            }
+            // ---- phase 2: all remaining column groups
+#pragma unroll
+            for (int j = jc + 2; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool lower = (i > j) || (i == j && p_low);
+                    const bool a_le = (i < jc) || (i == jc && p_ale);
+                    if (lower || a_le) reg[i][j] -= ua[i] * ub[j];
+                }
         }
     }
     __syncthreads();
-    if (tid < NB) {
-        const double piv = pivs[tid];
-        invd[tid] = 1.0 / sqrt(piv);
-    }
+    if (tid < NB) invd[tid] = 1.0 / sqrt(pivs[tid]);
     __syncthreads();
     // first bad pivot (if any), LAPACK style
     if (tid == 0) {
