@@ -38,6 +38,9 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-latents', type=int, default=1)
+    ap.add_argument('--emulators', type=int, default=64)      # cfg5_batch only
+    ap.add_argument('--threads', type=int, default=8)         # cfg5_batch only: host threads (streams) per GPU
+    ap.add_argument('--maxiter', type=int, default=30)        # cfg5_batch only: L-BFGS-B iteration budget per emulator
     return ap.parse_args()
 
 
@@ -240,7 +243,7 @@ def run_ours(args):
     # ---- stage breakdown: the same K steps with stage events recorded inside the C-ABI call (this
     #      makes the library join its stream groups between Cholesky and triangular inverse, so the
     #      stages sum to slightly more than ms_per_step) ----
-    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
     for evs in stage_ev:
         for e in evs:
             e.record()          # force creation of the underlying cudaEvent_t
@@ -248,7 +251,8 @@ def run_ours(args):
     for s in range(args.steps):
         device_step(stage_ev[s])
     barrier()
-    stages = np.array([[evs[i].elapsed_time(evs[i + 1]) for i in range(4)] for evs in stage_ev]).mean(axis=0)  # ms
+    # [build, cholesky, trtri, solve (pre-contract), contract kernel, tail] in ms
+    stages = np.array([[evs[i].elapsed_time(evs[i + 1]) for i in range(6)] for evs in stage_ev]).mean(axis=0)
     st = torch.tensor(stages, dtype=torch.float64, device=dev)
 
     # ---- e2e: public API, host parameters in, host objective + gradient out ----
@@ -270,9 +274,16 @@ def run_ours(args):
         peaks, psrc = measured_peaks()
         fp64_peak = dgemm_peak(dev)
         npad = _cabi.padded(n)
-        chol_flops = q_loc * n ** 3 / 3.0              # algorithmic, per launch of the Cholesky stage on one rank
-        chol_tf = chol_flops / (stages[1] * 1e-3) / 1e12
+        stage_flops = q_loc * n ** 3 / 3.0             # algorithmic flop of each of the three dense stages on one rank
+        tf = lambda ms: stage_flops / (ms * 1e-3) / 1e12
         build_bytes = 8.0 * q_loc * n * (n + 1) / 2     # lower triangle written
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_contract_kernel_traffic.json')
+        if os.path.exists(tpath):                       # dram bytes of this launch from the committed ncu capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get('q_loc') == q_loc and tj.get('n') == n:
+                traffic = tj['dram_bytes_per_launch']
         line = {
             'metric': 'NLL+grad evals/s', 'value': args.steps / t_dev, 'unit': 'evals/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_dev / args.steps * 1e3,
@@ -281,19 +292,22 @@ def run_ours(args):
             'e2e': {'value': args.steps / t_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': eng.h2d_bytes,
                     'd2h_bytes_per_step': eng.d2h_bytes if world == 1 else (1 + p + q * d + 2 * q) * 8},
             'gpu_launches': eng.launches_per_eval * args.steps,
-            'roofline': {'bound': 'tensor', 'kernel': 'batched blocked Cholesky stage (DMMA SYRK/TRSM GEMM + diagonal-block kernel)',
-                         'achieved': chol_tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': chol_tf / fp64_peak,
+            # dominant kernel: the fused A^-1 / gradient-contraction GEMM, one launch per step (largest
+            # single kernel, ~1/3 of the step); timed live with CUDA events recorded around the launch
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel<ContractJob> (A^-1 = U U^T tiles on DMMA + fused gradient contraction)',
+                         'achieved': tf(stages[4]), 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(stages[4]) / fp64_peak,
                          'peak_source': 'cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
-                         'flops_per_launch': chol_flops, 'traffic': None},
+                         'flops_per_launch': stage_flops, 'kernel_ms': float(stages[4]), 'traffic': traffic},
             'stages': {
                 'build_ms': float(stages[0]), 'cholesky_ms': float(stages[1]), 'trtri_ms': float(stages[2]),
-                'solve_contract_ms': float(stages[3]),
+                'solve_ms': float(stages[3]), 'contract_kernel_ms': float(stages[4]), 'tail_ms': float(stages[5]),
                 'build_gbs': build_bytes / (stages[0] * 1e-3) / 1e9, 'hbm_peak_gbs': peaks['hbm_gbs'],
                 'hbm_peak_source': psrc, 'build_frac_of_hbm': build_bytes / (stages[0] * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'cholesky_tflops': chol_tf, 'trtri_tflops': q_loc * n ** 3 / 3.0 / (stages[2] * 1e-3) / 1e12,
-                'contract_tflops': q_loc * n ** 3 / 3.0 / (stages[3] * 1e-3) / 1e12,
+                'cholesky_tflops': tf(stages[1]), 'cholesky_frac_of_dgemm': tf(stages[1]) / fp64_peak,
+                'trtri_tflops': tf(stages[2]), 'trtri_frac_of_dgemm': tf(stages[2]) / fp64_peak,
+                'contract_tflops': tf(stages[4]),
                 'whole_eval_tflops': q_loc * float(n) ** 3 / (t_dev / args.steps) / 1e12,
-                'padded_n': npad},
+                'dgemm_peak_tflops': fp64_peak, 'padded_n': npad},
             'clocks': clk, 'objective': f_e2e, 'grad_norm': float(np.linalg.norm(g_e2e)), 'ctor_s': t_ctor,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -315,9 +329,49 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+def run_batched(args):
+    """BASELINE config 5: 64 independent emulators (n=1024, d=6, p=64, q=8, seeds 1024..1087) fitted with a
+    fixed L-BFGS-B budget, emulator i on rank i mod N ("replicas only": no collective during the fit).
+    Prints its own JSON line (metric: emulator fits/s); not the headline bench line."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from lcgp_b200 import fit_emulators, synthetic
+    n_em = args.emulators
+    data, mk = [], None
+    for i in range(n_em):
+        x, y, _, _, mk = synthetic.make_config('cfg5_one', seed=1024 + i)
+        data.append((x, y))
+    fit_emulators(data[:min(2 * world, n_em)], mk, fit_options=dict(maxiter=3), threads_per_gpu=args.threads)   # warm-up
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = fit_emulators(data, mk, fit_options=dict(maxiter=args.maxiter), threads_per_gpu=args.threads)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        evals = sum(r['n_evals'] for r in res)
+        print(json.dumps({'metric': 'emulator fits/s', 'value': n_em / dt, 'unit': 'fits/s', 'n_gpus': world,
+                          'evals_per_s': evals / dt, 'total_evals': evals, 'wall_s': dt, 'dtype': 'f64', 'data': 'synthetic',
+                          'config': {'workload': f'cfg5: {n_em} emulators n=1024 d=6 p=64 q=8, L-BFGS-B maxiter={args.maxiter}',
+                                     'threads_per_gpu': args.threads}, 'scaling': 'replicas only',
+                          'mean_final_loss': float(np.mean([r['loss'] for r in res]))}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.config == 'cfg5_batch':
+        run_batched(a)
     else:
         run_ours(a)

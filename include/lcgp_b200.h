@@ -27,6 +27,7 @@ extern "C" {
 
 #define LCGP_NB 128
 #define LCGP_MAX_D 64
+#define LCGP_N_STAGE_EVENTS 7
 
 #define LCGP_E_ARG (-1)        /* null pointer / non-positive size */
 #define LCGP_E_DIM (-2)        /* d > LCGP_MAX_D or np not a multiple of LCGP_NB */
@@ -72,13 +73,17 @@ size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
  * autodiff driven from fit() (lcgp.py:537-540).  Parameters are the CONSTRAINED values:
  * lLmb (q_loc x d length-scales), lLmb0 (q_loc variances), lnugGPs (q_loc), lsigma2s expanded to
  * the p-vector of get_param (lcgp.py:515-532).
- * flags: bit0 = also compute the gradient (otherwise only out[0] and the diagnostics are valid).
+ * flags: bit0 = also compute the gradient (otherwise only out[0] and the diagnostics are valid);
+ *        bits 4-7 = number of internal stream groups the latents are factored on (0 = default min(4, q_loc);
+ *        1 = everything on `stream`, e.g. when the caller runs many small emulators on its own streams).
  * After the call the workspace holds L_k, L_k^{-T}, alpha_k (= CinvMs, lcgp.py:781) and m_k (= mks,
  * lcgp.py:779) for lcgp_predict / lcgp_get_aux -- i.e. it also replaces
  * _compute_aux_predictive_quantities_rep (lcgp.py:728-803) and compute_aux_predictive_quantities
  * (lcgp.py:685-726).
- * stage_events: NULL or 5 cudaEvent_t recorded at: start, after kernel-matrix build, after Cholesky,
- * after triangular inverse, end. */
+ * stage_events: NULL or LCGP_N_STAGE_EVENTS cudaEvent_t recorded at: [0] start, [1] after the
+ * kernel-matrix build, [2] after Cholesky, [3] after the triangular inverse, [4] before and [5] after the
+ * fused A^-1 / gradient-contraction GEMM launch (the single largest kernel), [6] end.  Passing events
+ * also makes the call join its internal stream groups between [2] and [3]. */
 int lcgp_nll_grad(const lcgp_problem* prob, const double* lLmb, const double* lLmb0, const double* lnugGPs,
                   const double* lsigma2_p, void* workspace, size_t workspace_bytes, double* out,
                   int32_t* info, int32_t flags, void* const* stage_events, void* stream);

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_lib', 'liblcgp_b200.so')
 NB = 128
 MAX_D = 64
+N_STAGE_EVENTS = 7
 
 _dp = C.c_void_p  # device / host pointers travel as integers
 

@@ -285,7 +285,8 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     // A_k
     LCGP_CUDA(launch_build_A(P->X, P->sr, n, d, w.np, kp, w.F, w.fstride, q, st));
     rec(1);
-    const int G = stream_groups(q);
+    int G = (flags >> 4) & 15;
+    G = G == 0 ? stream_groups(q) : (G > MAX_GROUPS ? MAX_GROUPS : (G > q ? q : G));
     auto potrf_group = [&](int g0, int cnt, cudaStream_t s) {
         return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
                              w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s);
@@ -315,13 +316,17 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     LCGP_CUDA(solve_alpha(v, a, st));
     double* g_kern = out + 1 + p;
     if (with_grad) {
-        LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, g_kern + (size_t)q * d, g_kern + (size_t)q * d + q, st));
+        LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, g_kern + (size_t)q * d, g_kern + (size_t)q * d + q,
+                                ev ? (cudaEvent_t)ev[4] : nullptr, ev ? (cudaEvent_t)ev[5] : nullptr, st));
         zmat_kernel<8><<<dim3((p + 7) / 8, (q + 7) / 8), 256, 0, st>>>(n, w.np, p, q, P->YR, w.mk, w.Z);
         LCGP_CUDA(cudaGetLastError());
+    } else {
+        rec(4);
+        rec(5);
     }
     finalize_kernel<<<1, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
     LCGP_CUDA(cudaGetLastError());
-    rec(4);
+    rec(6);
     return 0;
 }
 

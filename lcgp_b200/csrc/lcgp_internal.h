@@ -45,7 +45,8 @@ struct SolveArgs {
 };
 cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream);
 cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part /* q_loc x ntiles x (d+2) */,
-                          double* g_ell, double* g_s0, double* g_lnug, cudaStream_t stream);
+                          double* g_ell, double* g_s0, double* g_lnug, cudaEvent_t ev_before, cudaEvent_t ev_after,
+                          cudaStream_t stream);
 
 // predict.cu
 cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,

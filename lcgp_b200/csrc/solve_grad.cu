@@ -274,10 +274,13 @@ __global__ void contract_reduce_kernel(int ntiles, int d, const double* __restri
 }
 
 cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part, double* g_ell,
-                          double* g_s0, double* g_lnug, cudaStream_t stream) {
+                          double* g_s0, double* g_lnug, cudaEvent_t ev_before, cudaEvent_t ev_after,
+                          cudaStream_t stream) {
     const int ntiles = v.nb * (v.nb + 1) / 2;
     ContractParams p{v, a.n, a.d, a.X, a.sr, a.alpha, a.kp, tile_part, ntiles};
+    if (ev_before) cudaEventRecord(ev_before, stream);
     cudaError_t e = gemm_launch<ContractJob>(p, dim3(ntiles, a.q_loc, 1), stream);
+    if (ev_after) cudaEventRecord(ev_after, stream);
     if (e != cudaSuccess) return e;
     contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
     return cudaGetLastError();

@@ -74,8 +74,10 @@ class _NegLogPost(torch.autograd.Function):
 class CudaEngine:
     """Device-resident constant data of this rank's latents + the C-ABI calls on them."""
 
-    def __init__(self, n, d, p, X, sr, YR, w, t, phi_loc, D_loc, scale, sum_log_r, include_host_terms, device=None):
+    def __init__(self, n, d, p, X, sr, YR, w, t, phi_loc, D_loc, scale, sum_log_r, include_host_terms, device=None,
+                 stream_groups=0):
         _cabi.require_cuda()
+        self.group_flags = (int(stream_groups) & 15) << 4   # 0 = library default (see include/lcgp_b200.h)
         self.lib = _cabi.lib()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.n, self.d, self.p = int(n), int(d), int(p)
@@ -140,7 +142,7 @@ class CudaEngine:
         if events is None:
             return None
         import ctypes as C
-        arr = (C.c_void_p * 5)(*[int(e.cuda_event) for e in events])
+        arr = (C.c_void_p * _cabi.N_STAGE_EVENTS)(*[int(e.cuda_event) for e in events])
         return arr
 
     def evaluate(self, lLmb, lLmb0, lnug, lsig_p, with_grad=True, events=None):
@@ -151,8 +153,8 @@ class CudaEngine:
         with torch.cuda.device(self.device):
             rc = self.lib.lcgp_nll_grad_host(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
                                              self.ws.data_ptr(), self.ws_bytes, self.h_out.data_ptr(),
-                                             self.h_info.data_ptr(), int(bool(with_grad)), self._events_arg(events),
-                                             _cabi.stream_ptr())
+                                             self.h_info.data_ptr(), int(bool(with_grad)) | self.group_flags,
+                                             self._events_arg(events), _cabi.stream_ptr())
         _cabi.check(rc, 'lcgp_nll_grad_host')
         self._check_info(self.h_info)
         return self.h_out.clone()
@@ -166,8 +168,8 @@ class CudaEngine:
             base = self.d_par.data_ptr()
             rc = self.lib.lcgp_nll_grad(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
                                         self.ws.data_ptr(), self.ws_bytes, self.d_out.data_ptr(),
-                                        self.d_info.data_ptr(), int(bool(with_grad)), self._events_arg(events),
-                                        _cabi.stream_ptr())
+                                        self.d_info.data_ptr(), int(bool(with_grad)) | self.group_flags,
+                                        self._events_arg(events), _cabi.stream_ptr())
         _cabi.check(rc, 'lcgp_nll_grad')
         return self.d_out
 
@@ -222,13 +224,14 @@ class LCGP:
     works on (x_unique, ybar).  Constructor arguments, attributes, methods and raised exception
     types follow lcgp.py:31-41 and the reference test-suite; tensors are torch.float64.
     Extra keyword arguments (not in the reference): `device`, `engine_factory` (tests only),
-    `shard` (shard latents over torch.distributed ranks when a process group is initialised).
+    `shard` (shard latents over torch.distributed ranks when a process group is initialised),
+    `stream_groups` (internal CUDA stream groups per evaluation; 0 = library default).
     """
 
     def __init__(self, y=None, x=None, q: int = None, var_threshold: float = None,
                  diag_error_structure: list = None, parameter_clamp_flag: bool = False,
                  robust_mean: bool = True, submethod: str = 'full', rep_standardize_ybar: bool = True,
-                 verbose: bool = False, device=None, shard: bool = True, engine_factory=None):
+                 verbose: bool = False, device=None, shard: bool = True, engine_factory=None, stream_groups: int = 0):
         self.verbose = verbose
         self.robust_mean = robust_mean
         self.rep_standardize_ybar = rep_standardize_ybar
@@ -236,6 +239,7 @@ class LCGP:
         self._device = device
         self._engine_factory = engine_factory
         self._engine = None
+        self._stream_groups = stream_groups
 
         self.x = _as_tensor2d(x)
         self.y = _as_tensor2d(y)
@@ -527,7 +531,7 @@ class LCGP:
                 self._engine = False      # this rank owns no latent
             else:
                 factory = self._engine_factory or CudaEngine
-                kw = {} if self._engine_factory else dict(device=self._device)
+                kw = {} if self._engine_factory else dict(device=self._device, stream_groups=self._stream_groups)
                 self._engine = factory(phi_loc=self.phi[:, idx], D_loc=self.diag_D[idx],
                                        include_host_terms=(self._rank == 0), **data, **kw)
         return self._engine

@@ -351,3 +351,55 @@ def test_properties_at_config3_scale():
     assert abs((fp - fm) / (2 * h) - g @ dirn) <= 1e-5 * max(1.0, abs(g @ dirn))
     yp, ypv, ycv = m.predict(x0)
     assert torch.isfinite(yp).all() and (ypv > 0).all() and (ycv <= ypv + 1e-9).all() and (ycv > -1e-9).all()
+
+
+# ---------------------------------------------------------------- config 5: batched independent fits
+def test_fit_emulators_matches_sequential_fits():
+    from lcgp_b200 import fit_emulators, perturbed_restart
+    data = [make_full_data(seed=100 + i, n=90, p=4, d=2) for i in range(6)]
+    mk = dict(q=2, submethod='full')
+    opts = dict(maxiter=15)
+    res = fit_emulators(data, mk, fit_options=opts, threads_per_gpu=3)
+    assert [r['index'] for r in res] == list(range(6))
+    for i in (0, 5):                                   # concurrency must not change any emulator's answer
+        m = LCGP(y=data[i][1], x=data[i][0], **mk)
+        m.fit(**opts)
+        assert abs(float(m.loss()) - res[i]['loss']) <= 1e-9 * abs(res[i]['loss'])
+        assert rel(m.lLmb.numpy(), res[i]['lLmb']) < 1e-7
+    # multi-start on one data set: different starts, all finite
+    res2, models = fit_emulators([data[0]] * 3, mk, fit_options=opts, threads_per_gpu=3,
+                                 init_hooks=[None, perturbed_restart(1), perturbed_restart(2)], return_models=True)
+    assert len(models) == 3 and all(np.isfinite(r['loss']) for r in res2)
+
+
+# ---------------------------------------------------------------- edge cases of the C-ABI / kernels
+@pytest.mark.parametrize('n,d,q', [(3, 1, 1), (127, 2, 2), (128, 2, 2), (257, 64, 1), (1000, 3, 9)])
+def test_edge_shapes(n, d, q):
+    """Tiny n, n at / just over a block boundary, the maximum input dimension, q not a multiple of 8."""
+    rng = np.random.default_rng(n + d)
+    p = max(q, 3)
+    x = rng.uniform(0, 1, (n, d))
+    y = np.sin(x @ rng.standard_normal((d, p))).T + 0.1 * rng.standard_normal((p, n))
+    m, o = _pair(x, y, q=q, submethod='full')
+    _check_loss_grad(m, o, o.neglpost_chol)
+    x0 = rng.uniform(0, 1, (5, d))
+    for a, b in zip(m.predict(x0), o.predict(torch.as_tensor(x0))):
+        assert rel(a, b) < PRED_TOL
+
+
+def test_input_dimension_limit_is_reported():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (40, 65)); y = rng.standard_normal((3, 40))
+    m = LCGP(y=y, x=x, q=2)
+    with pytest.raises(ValueError, match='d <= 64'):
+        m.loss()
+    L = _cabi.lib()
+    assert L.lcgp_kernel_matrix(1, 4, 1, 4, 65, 1, 1, 1, 0, 1, None) == -2      # LCGP_E_DIM before any dereference
+
+
+def test_nan_input_is_reported_not_silently_used():
+    x, y = make_full_data(seed=3, n=60, p=3, d=2)
+    m = LCGP(y=y, x=x, q=2)
+    m.lLmb0.unconstrained.data[0] = float('nan')
+    with pytest.raises(RuntimeError, match='Cholesky failed'):
+        m.loss()
