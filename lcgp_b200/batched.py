@@ -75,11 +75,18 @@ def fit_emulators(datasets: Sequence[tuple], model_kwargs: dict | Sequence[dict]
                 with lock:
                     errors.append((i, ex))
 
-    threads = [threading.Thread(target=worker) for _ in range(max(1, min(threads_per_gpu, len(mine))))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    # Host-side preprocessing of a small emulator (sort, SVD of a p x n matrix) is slower with many
+    # intra-op threads than with one, and several emulators are preprocessed concurrently anyway.
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        threads = [threading.Thread(target=worker) for _ in range(max(1, min(threads_per_gpu, len(mine))))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        torch.set_num_threads(prev_threads)
     if errors:
         raise RuntimeError(f'fit_emulators: emulator {errors[0][0]} failed: {errors[0][1]!r}') from errors[0][1]
 
