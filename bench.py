@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--config', default='cfg4_rep')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end fit() wall-time measurement')
+    ap.add_argument('--fit-config', default='cfg3_rep')
     ap.add_argument('--cpu-sample-latents', type=int, default=1)
     ap.add_argument('--emulators', type=int, default=64)      # cfg5_batch only
     ap.add_argument('--threads', type=int, default=8)         # cfg5_batch only: host threads (streams) per GPU
@@ -156,6 +158,38 @@ def cpu_baseline_sample(x, y, mk, n_latents, q, threads):
     o.loss_and_grad(fn)
     dt = time.time() - t0
     return o, fn, dt
+
+
+def fit_wall(cfg_name, with_cpu):
+    """End-to-end fit() wall time (BASELINE metric 'fit wall-s') on a configuration whose CPU cost is
+    affordable: constructor excluded, SciPy L-BFGS-B defaults, then one oracle evaluation on the host
+    cores to extrapolate the reference's fit time as evals x per-eval (labelled as such)."""
+    from lcgp_b200 import LCGP, synthetic
+    x, y, x0, y0, mk = synthetic.make_config(cfg_name)
+    m = LCGP(y=y, x=x, **mk)
+    m.loss_and_grad()                       # workspace allocation / first-touch outside the timed region
+    m.n_evals = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.fit()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    out = {'config': cfg_name, 'n': int(m.n), 'q': int(m.q), 'wall_s': wall, 'evals': m.n_evals,
+           'final_loss': float(m.loss()), 'optimizer': 'L-BFGS-B (SciPy defaults)'}
+    if with_cpu:
+        try:
+            from oracle.lcgp_oracle import LCGPOracle
+            torch.set_num_threads(os.cpu_count() or 1)
+            o = LCGPOracle(y=y, x=x, skip_xnorm=True, **mk)
+            fn = o.neglpost_chol if mk['submethod'] == 'full' else None
+            t1 = time.perf_counter()
+            o.loss_and_grad(fn)
+            per_eval = time.perf_counter() - t1
+            out['cpu_port_s_per_eval'] = per_eval
+            out['cpu_port_fit_s_extrapolated'] = per_eval * m.n_evals
+        except Exception as ex:
+            out['cpu_port_s_per_eval'] = f'failed: {ex!r}'
+    return out
 
 
 def run_reference(args):
@@ -323,6 +357,8 @@ def run_ours(args):
                                         'sample': f'failed: {ex!r}'}
         else:
             line['cpu_baseline'] = None
+        if world == 1 and not args.no_fit:
+            line['fit'] = fit_wall(args.fit_config, not args.no_cpu_baseline)
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
