@@ -668,6 +668,36 @@ class LCGP:
         self._invalidate_aux()
         return
 
+    # ------------------------------------------------------------------ state save / restore
+    def state_dict(self):
+        """Fitted state (the reference has no checkpointing): the four parameter tensors
+        in unconstrained form plus the data fingerprint they belong to."""
+        return {'format': 'lcgp_b200/1', 'submethod': self.submethod, 'q': int(self.q), 'n': int(self.n),
+                'd': int(self.d), 'p': int(self.p), 'diag_error_structure': list(self.diag_error_structure),
+                'diag_D': self.diag_D.clone(), 'x_checksum': self._x_checksum(),
+                'params': {k: getattr(self, k).unconstrained.detach().clone()
+                           for k in ('lLmb', 'lLmb0', 'lsigma2s', 'lnugGPs')}}
+
+    def _x_checksum(self):
+        X = self.x_unique_s if self.submethod == 'rep' else self.x
+        wgt = torch.arange(1, X.numel() + 1, dtype=DT).reshape(X.shape)
+        return float((X * wgt).sum())
+
+    def load_state_dict(self, state):
+        """Restore parameters saved by state_dict() into a model built on the same data."""
+        for k in ('submethod', 'q', 'n', 'd', 'p'):
+            if state[k] != (getattr(self, k) if k == 'submethod' else int(getattr(self, k))):
+                raise ValueError(f'state_dict mismatch in {k!r}: {state[k]} vs {getattr(self, k)}')
+        if list(state['diag_error_structure']) != list(self.diag_error_structure) or \
+                not torch.allclose(state['diag_D'], self.diag_D, rtol=1e-10, atol=0) or \
+                abs(state['x_checksum'] - self._x_checksum()) > 1e-9 * max(1.0, abs(state['x_checksum'])):
+            raise ValueError('state_dict was saved for different data / error structure')
+        with torch.no_grad():
+            for k, v in state['params'].items():
+                getattr(self, k).unconstrained.copy_(v)
+        self._invalidate_aux()
+        return self
+
     # ------------------------------------------------------------------ aux predictive quantities
     def _invalidate_aux(self):
         self._factor_key = None

@@ -183,3 +183,17 @@ def test_synthetic_configs_shapes():
     assert x.shape == (1024, 6) and y.shape == (64, 1024) and mk['q'] == 8
     x, y, x0, y0, mk = synthetic.make_config('cfg3_rep', n=100)
     assert np.unique(x, axis=0).shape[0] == 100 and y.shape[0] == 500
+
+
+def test_state_dict_roundtrip(tmp_path):
+    x, y = make_full_data(n=30, p=3, d=2)
+    a = LCGP(y=y, x=x, q=2)
+    a.lLmb.assign(a.lLmb.numpy() * 1.7); a.lsigma2s.assign([-1.0, -2.0, -3.0])
+    torch.save(a.state_dict(), tmp_path / 'm.pt')
+    b = LCGP(y=y, x=x, q=2).load_state_dict(torch.load(tmp_path / 'm.pt'))
+    for pa, pb in zip(a.get_param(), b.get_param()):
+        assert torch.equal(pa, pb)
+    with pytest.raises(ValueError):
+        LCGP(y=y, x=x, q=3).load_state_dict(a.state_dict())
+    with pytest.raises(ValueError):
+        LCGP(y=y * 2.0 + 1.0, x=x[::-1].copy(), q=2).load_state_dict(a.state_dict())
