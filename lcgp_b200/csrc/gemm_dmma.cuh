@@ -1,41 +1,115 @@
 // Batched 128x128-tile FP64 GEMM on the Blackwell FP64 tensor pipe (mma.sync m8n8k4 -> DMMA.8x8x4).
 //
-// One CTA (8 warps, warp tile 64x32, 64 accumulator doubles per thread) produces one 128x128
-// tile  acc[m][n] = sum_k A[m][k] * B[n][k].  Operand A is always K-major (row m contiguous in
-// k); operand B is K-major or N-major (B[k][n], row k contiguous in n).  Tiles are staged through
-// a 3-deep cp.async ring (32-deep K stages) in shared memory with padded pitches chosen so that every DMMA fragment
-// load (LDS.64) is bank-conflict free.  The K range is a run of NB-wide blocks [kb0, kb1); a Job
-// supplies the tile base pointer per K block (so triangular operands can switch between the big
-// factor buffer and the dense diagonal-block arrays) and an epilogue that consumes the register
-// accumulators (store, read-modify-write, or a fused reduction).
+// One CTA (8 warps, warp tile 64x32, 64 accumulator doubles per thread) produces one 128x128 tile
+// acc[m][n] = sum_k A[m][k] * B[n][k].  Operand A is always K-major (row m contiguous in k); operand B
+// is K-major or N-major (B[k][n], row k contiguous in n).  The K range is a run of NB-wide blocks
+// [kb0, kb1); a Job names, per K block, the 128x128 source region of each operand (TileRef: which
+// buffer, top-left row / column) -- so triangular operands can switch between the big factor buffer
+// and the dense diagonal-block arrays and skip structurally-zero blocks -- and supplies an epilogue
+// that consumes the register accumulators (store, read-modify-write, or a fused reduction).
+//
+// Two staging engines feed the same MMA code:
+//   gemm_tma_kernel  : TMA tensor tiles (cp.async.bulk.tensor, SASS UTMALDG) with the 128-byte swizzle into a
+//                      3-deep mbarrier full/empty ring; one elected lane issues 4 (K-major B) or 10
+//                      (N-major B) box loads per 32-deep K stage; no CTA-wide barrier in the K loop.
+//                      DMMA fragment loads stay bank-conflict free because fragment rows / columns are
+//                      PERMUTED (see TmaCoord): the swizzle XORs the 16-byte chunk index with row % 8,
+//                      so the four rows a half-warp touches must differ in bits 1-2, not bit 0.
+//   gemm_dmma_kernel : cp.async (LDGSTS) into padded tiles, one barrier per stage (fallback engine).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace lcgp {
 
+// ---------------------------------------------------------------------------------------------
+// Operand sources
+// ---------------------------------------------------------------------------------------------
+enum { SRC_F = 0, SRC_DU = 1, SRC_DL = 2, SRC_T = 3, SRC_C = 4, NSRC = 5 };
+
+struct TileRef { int src, row, col; };   // top-left of a 128 x 128 region inside one batch element of `src`
+
+struct GemmSrcs {                         // pointer view (batch element b starts at base + b * bstride)
+    const double* base[NSRC];
+    int ld[NSRC];
+    size_t bstride[NSRC];
+};
+
+struct GemmMaps {                         // TMA view: 3-D maps (column, row, batch) of the same buffers
+    CUtensorMap km[NSRC];                 // box 16 x 128 x 1  (K-major operand: 16 k-columns of 128 rows)
+    CUtensorMap nm[2];                    // box 16 x 32 x 1   (N-major operand from SRC_F / SRC_DU)
+};
+
+// Storage convention for one latent's factor buffer F (np x np, row-major, np % NB == 0):
+//   strictly-lower NB-blocks and the lower triangle of diagonal blocks : L   (A = L L^T)
+//   strictly-upper NB-blocks                                           : U = L^{-T} (U[i][k] = W[k][i], W = L^{-1})
+//   DL[b], DU[b] (dense NB x NB, explicit zeros)                        : inverse of diagonal block b and its transpose
+struct FactorView {
+    double* F;          // batch base
+    const double* DL;   // batch base, nb * NB * NB per matrix
+    const double* DU;
+    int np, nb;
+    size_t fstride, dstride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Accumulator <-> tile coordinates
+// ---------------------------------------------------------------------------------------------
+// cp.async engine: natural m8n8k4 layout.  lane = 4 g + t : a = A[g][t], b = B[t][g], d = D[g][2t, 2t+1]
 struct WarpCoord {
+    static constexpr bool kPairs = true;   // a lane's two accumulator columns are adjacent
     int wm, wn, g, t;
     __device__ __forceinline__ WarpCoord() {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        wm = warp >> 2;  // 0..1  -> 64-row slab
-        wn = warp & 3;   // 0..3  -> 32-col slab
-        g = lane >> 2;   // fragment row / col group
-        t = lane & 3;    // fragment k index / col pair
+        wm = warp >> 2;
+        wn = warp & 3;
+        g = lane >> 2;
+        t = lane & 3;
     }
     __device__ __forceinline__ int row(int mi) const { return wm * 64 + mi * 8 + g; }
-    __device__ __forceinline__ int col(int ni) const { return wn * 32 + ni * 8 + 2 * t; }
+    __device__ __forceinline__ int col(int ni, int e) const { return wn * 32 + ni * 8 + 2 * t + e; }
 };
 
+// TMA engine: MMA row g of an 8-row group sits in tile row perm8(g) = 2 (g % 4) + g / 4, so that the
+// rows of a half-warp (g = 0..3 or 4..7) are {0,2,4,6} / {1,3,5,7} and the A fragment loads are
+// conflict free.  A K-major B operand keeps the natural n order instead (its 4 fragment loads per k-step
+// are then 2-way conflicted, which costs 4 extra LDS wavefronts per 32 DMMAs) so that a lane's two
+// accumulator columns stay adjacent for 16-byte epilogue accesses; an N-major B operand spreads the 8 n
+// of an MMA over two 16-byte chunk groups of a 16-wide box: conflict free AND adjacent.
+__device__ __forceinline__ int perm8(int g) { return ((g & 3) << 1) | (g >> 2); }
+
+template <bool BNMAJOR>
+struct TmaCoord {
+    static constexpr bool kPairs = true;
+    int wm, wn, g, t, pg;
+    __device__ __forceinline__ TmaCoord() {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        wm = warp >> 2;
+        wn = warp & 3;
+        g = lane >> 2;
+        t = lane & 3;
+        pg = perm8(g);
+    }
+    __device__ __forceinline__ int row(int mi) const { return wm * 64 + mi * 8 + pg; }
+    __device__ __forceinline__ int col(int ni, int e) const {
+        if (BNMAJOR) return wn * 32 + 16 * (ni >> 1) + 4 * (ni & 1) + ((t & 1) << 3) + (t & 2) + e;   // {0,8,2,10}[t]
+        return wn * 32 + ni * 8 + 2 * t + e;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// cp.async engine
+// ---------------------------------------------------------------------------------------------
 template <class Job>
-__device__ __forceinline__ void gemm_load_stage(const typename Job::Params& p, const Job& job, int it,
-                                                unsigned As, unsigned Bs) {
+__device__ __forceinline__ void gemm_load_stage(const typename Job::Params& p, const Job& job, const GemmSrcs& s,
+                                                int it, unsigned As, unsigned Bs) {
     const int kb = job.kb0 + it / KSTEPS;
     const int ks = it % KSTEPS;
-    const double* pa;
-    const double* pb;
-    int lda, ldb;
-    job.a_src(p, kb, pa, lda);
-    job.b_src(p, kb, pb, ldb);
+    const TileRef ra = job.a_ref(p, kb), rb = job.b_ref(p, kb);
+    const int lda = s.ld[ra.src], ldb = s.ld[rb.src];
+    const double* pa = s.base[ra.src] + (size_t)blockIdx.y * s.bstride[ra.src] + (size_t)ra.row * lda + ra.col;
+    const double* pb = s.base[rb.src] + (size_t)blockIdx.y * s.bstride[rb.src] + (size_t)rb.row * ldb + rb.col;
     const int tid = threadIdx.x;
     constexpr int CPR = BK / 2;                       // 16-byte chunks per K-major tile row
     constexpr int NCH = NB * CPR / GEMM_THREADS;      // chunks per thread per operand
@@ -81,29 +155,28 @@ __device__ __forceinline__ void gemm_compute_stage(const double* __restrict__ As
     }
 }
 
-// Runs the pipelined K loop of `job` and leaves the tile in `acc`.  On return all cp.async
-// groups have drained and all threads have passed a barrier, so `smem` may be reused.
-// One barrier per BK-deep stage; the loads for stage it+STAGES-1 (which overwrite the buffer
-// consumed in iteration it-1, free since the barrier) are issued after the first quarter of the
-// stage's MMAs so that the tensor pipe already has work queued while the LSU issues them.
+// One barrier per BK-deep stage; the loads for stage it+STAGES-1 (which overwrite the buffer consumed in
+// iteration it-1, free since the barrier) are issued after the first quarter of the stage's MMAs.
 template <class Job>
-__device__ __forceinline__ void gemm_mainloop(const typename Job::Params& p, const Job& job,
-                                              double (&acc)[8][4][2], double* smem, const WarpCoord& wc) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const typename Job::Params p, const GemmSrcs srcs) {
+    extern __shared__ __align__(16) double smem[];
+    Job job;
+    if (!job.init(p)) return;
+    WarpCoord wc;
+    double acc[8][4][2];
     constexpr int B_STAGE = Job::kBNMajor ? BN_STAGE : A_STAGE;
     constexpr int KK = BK / 4;
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
-    const unsigned As_u = (unsigned)__cvta_generic_to_shared(As);
-    const unsigned Bs_u = (unsigned)__cvta_generic_to_shared(Bs);
+    const unsigned As_u = smem_u32(As), Bs_u = smem_u32(Bs);
     const int niter = (job.kb1 - job.kb0) * KSTEPS;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < niter) gemm_load_stage<Job>(p, job, s, As_u + s * A_STAGE * 8, Bs_u + s * B_STAGE * 8);
+        if (s < niter) gemm_load_stage<Job>(p, job, srcs, s, As_u + s * A_STAGE * 8, Bs_u + s * B_STAGE * 8);
         cp_async_commit();
     }
     int cur = 0, nst = STAGES - 1;
@@ -112,7 +185,7 @@ __device__ __forceinline__ void gemm_mainloop(const typename Job::Params& p, con
         __syncthreads();
         gemm_compute_stage<Job::kBNMajor, 0, KK / 4>(As + cur * A_STAGE, Bs + cur * B_STAGE, acc, wc);
         const int nxt = it + STAGES - 1;
-        if (nxt < niter) gemm_load_stage<Job>(p, job, nxt, As_u + nst * A_STAGE * 8, Bs_u + nst * B_STAGE * 8);
+        if (nxt < niter) gemm_load_stage<Job>(p, job, srcs, nxt, As_u + nst * A_STAGE * 8, Bs_u + nst * B_STAGE * 8);
         cp_async_commit();
         gemm_compute_stage<Job::kBNMajor, KK / 4, KK>(As + cur * A_STAGE, Bs + cur * B_STAGE, acc, wc);
         cur = (cur + 1 == STAGES) ? 0 : cur + 1;
@@ -120,45 +193,191 @@ __device__ __forceinline__ void gemm_mainloop(const typename Job::Params& p, con
     }
     cp_async_wait<0>();
     __syncthreads();
-}
-
-template <class Job>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const typename Job::Params p) {
-    extern __shared__ __align__(16) double smem[];
-    Job job;
-    if (!job.init(p)) return;
-    WarpCoord wc;
-    double acc[8][4][2];
-    gemm_mainloop<Job>(p, job, acc, smem, wc);
     job.epilogue(p, acc, smem, wc);
 }
 
-template <class Job>
-inline cudaError_t gemm_launch(const typename Job::Params& p, dim3 grid, cudaStream_t stream) {
-    constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
-    static bool configured = false;  // per-process, per-Job; attribute is idempotent
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_dmma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
+// ---------------------------------------------------------------------------------------------
+// TMA engine
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_BOX_K = 16;                                  // doubles per swizzled 128-byte row
+constexpr int TMA_OPERAND_BYTES = NB * BK * 8;                 // 32 KB per operand per stage
+constexpr int TMA_STAGE_BYTES = 2 * TMA_OPERAND_BYTES;         // 64 KB
+constexpr size_t GEMM_SMEM_TMA = (size_t)STAGES * TMA_STAGE_BYTES + 64 + 1024;   // + mbarriers + alignment slack
+
+__device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
+}
+
+// K-major operand tile in shared memory: 2 boxes (k 0..15 | 16..31) of [128 rows][128 B], chunk ^= row % 8.
+// N-major operand tile: 8 boxes (16 n each) of [32 k rows][128 B].
+template <bool BNMAJOR>
+__device__ __forceinline__ void tma_compute_stage(const unsigned char* __restrict__ As, const unsigned char* __restrict__ Bs,
+                                                  double (&acc)[8][4][2], const TmaCoord<BNMAJOR>& wc) {
+    const int arow = (wc.wm * 64 + wc.pg) * 128;      // + mi * 1024
+    const int brow = (wc.wn * 32 + wc.g) * 128;       // K-major B (natural row order): + ni * 1024
+    // N-major B: column c = nperm(ni & 1, g) inside box (wn * 2 + ni / 2)
+    const int cn0 = (wc.g & 1) + ((wc.g & 2) << 2) + ((wc.g & 4) >> 1);
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[8], b[4];
+        const int akoff = (kk >> 2) * (NB * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.pg) << 4) + ((wc.t & 1) << 3);
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = *reinterpret_cast<const double*>(As + arow + mi * 1024 + akoff);
+        if (!BNMAJOR) {
+            const int bkoff = (kk >> 2) * (NB * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.g) << 4) + ((wc.t & 1) << 3);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double*>(Bs + brow + ni * 1024 + bkoff);
+        } else {
+            const int k = kk * 4 + wc.t;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = cn0 + 4 * (ni & 1);
+                b[ni] = *reinterpret_cast<const double*>(Bs + (wc.wn * 2 + (ni >> 1)) * (BK * 128) + k * 128 +
+                                                         (((c >> 1) ^ (k & 7)) << 4) + ((c & 1) << 3));
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
-    gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p);
+}
+
+template <class Job>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_constant__ GemmMaps maps) {
+    extern __shared__ unsigned char smem_raw[];
+    Job job;
+    if (!job.init(p)) return;   // uniform over the CTA
+    unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms are 1 KB
+    const unsigned sm_u = smem_u32(sm);
+    const unsigned full0 = sm_u + STAGES * TMA_STAGE_BYTES, empty0 = full0 + 8 * STAGES;
+    if (threadIdx.x == 32) {   // hide the first descriptor fetches behind the barrier set-up
+        const TileRef ra = job.a_ref(p, job.kb0), rb = job.b_ref(p, job.kb0);
+        tma_prefetch_desc(&maps.km[ra.src]);
+        tma_prefetch_desc(Job::kBNMajor ? &maps.nm[rb.src == SRC_F ? 0 : 1] : &maps.km[rb.src]);
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);                  // one arrive.expect_tx per fill
+            mbar_init(empty0 + 8 * s, GEMM_THREADS / 32); // one arrive per MMA warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int niter = (job.kb1 - job.kb0) * KSTEPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // fill iteration `nxt` into ring slot `slot` (`use` = earlier fills of that slot); one lane issues it
+    auto produce = [&](int nxt, int slot, int use) {
+        if (lane == 0) {
+            mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);   // passes at once for the first fill
+            mbar_arrive_expect_tx(full0 + 8 * slot, TMA_STAGE_BYTES);
+            const int kb = job.kb0 + nxt / KSTEPS, ks = nxt % KSTEPS;
+            const TileRef ra = job.a_ref(p, kb), rb = job.b_ref(p, kb);
+            const unsigned dA = sm_u + slot * TMA_STAGE_BYTES, dB = dA + TMA_OPERAND_BYTES;
+            const unsigned fb = full0 + 8 * slot;
+            const int bz = blockIdx.y;
+#pragma unroll
+            for (int h = 0; h < BK / TMA_BOX_K; ++h)
+                tma_load_3d(dA + h * (NB * 128), &maps.km[ra.src], ra.col + ks * BK + h * TMA_BOX_K, ra.row, bz, fb);
+            if (!Job::kBNMajor) {
+#pragma unroll
+                for (int h = 0; h < BK / TMA_BOX_K; ++h)
+                    tma_load_3d(dB + h * (NB * 128), &maps.km[rb.src], rb.col + ks * BK + h * TMA_BOX_K, rb.row, bz, fb);
+            } else {
+                const CUtensorMap* mb = &maps.nm[rb.src == SRC_F ? 0 : 1];
+#pragma unroll
+                for (int j = 0; j < NB / TMA_BOX_K; ++j)
+                    tma_load_3d(dB + j * (BK * 128), mb, rb.col + j * TMA_BOX_K, rb.row + ks * BK, bz, fb);
+            }
+        }
+        __syncwarp();
+    };
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < niter) produce(s, s, 0);
+    }
+
+    TmaCoord<Job::kBNMajor> wc;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    int st = 0, nslot = STAGES - 1, nuse = 0;
+    unsigned ph = 0;
+    for (int it = 0; it < niter; ++it) {
+        const int nxt = it + STAGES - 1;
+        if (nxt < niter && warp == (it & 7)) produce(nxt, nslot, nuse);   // the MMA warps take turns as producer
+        mbar_wait(full0 + 8 * st, ph);
+        tma_compute_stage<Job::kBNMajor>(sm + st * TMA_STAGE_BYTES, sm + st * TMA_STAGE_BYTES + TMA_OPERAND_BYTES, acc, wc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+        if (++nslot == STAGES) { nslot = 0; ++nuse; }
+    }
+    __syncthreads();   // every warp is done with the tiles: the epilogue may reuse shared memory
+    job.epilogue(p, acc, reinterpret_cast<double*>(sm), wc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: sources, tensor maps, launch
+// ---------------------------------------------------------------------------------------------
+struct GemmCtx {
+    GemmSrcs srcs;
+    GemmMaps maps;
+    bool tma;        // maps are valid and the TMA engine is selected
+};
+
+bool gemm_use_tma();   // engine selection (env LCGP_GEMM=tma|cpasync), defined in potrf.cu
+// Fills ctx.srcs from the arguments and, when the TMA engine is selected, encodes the tensor maps.
+// rows[] = rows per batch element of each source (0 = source unused).
+cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSRC], int batch);
+
+template <class Job>
+inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p, dim3 grid, cudaStream_t stream) {
+    if (ctx.tma) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_TMA);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
+    } else {
+        constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_dmma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p, ctx.srcs);
+    }
     return cudaGetLastError();
 }
 
-// -------------------------------------------------------------------------------------------
-// Storage convention for one latent's factor buffer F (np x np, row-major, np % NB == 0):
-//   strictly-lower NB-blocks and the lower triangle of diagonal blocks : L   (A = L L^T)
-//   strictly-upper NB-blocks                                           : U = L^{-T} (U[i][k] = W[k][i], W = L^{-1})
-//   DL[b], DU[b] (dense NB x NB, explicit zeros)                        : inverse of diagonal block b and its transpose
-// -------------------------------------------------------------------------------------------
-struct FactorView {
-    double* F;          // batch base
-    const double* DL;   // batch base, nb * NB * NB per matrix
-    const double* DU;
-    int np, nb;
-    size_t fstride, dstride;
-};
+// Stores one accumulator pair of a tile to row-major C (ld in doubles) for either coordinate layout.
+template <class Coord>
+__device__ __forceinline__ void store_pair(double* C, size_t ld, const Coord& wc, int mi, int ni, double v0, double v1) {
+    double* q = C + (size_t)wc.row(mi) * ld;
+    if (Coord::kPairs) {
+        *reinterpret_cast<double2*>(q + wc.col(ni, 0)) = make_double2(v0, v1);
+    } else {
+        q[wc.col(ni, 0)] = v0;
+        q[wc.col(ni, 1)] = v1;
+    }
+}
 
 // ---- Cholesky updates:  C[I][J] -= sum_{kb in [kb0,kb1)} P_I,kb P_J,kb^T ------------------------
 //   col <  0 : trailing update, all tiles jstart <= J <= I < nb (lower triangle of the trailing matrix)
@@ -186,25 +405,26 @@ struct SyrkJob {
         base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = base + (size_t)I * NB * p.v.np + (size_t)kb * NB;
-        ld = p.v.np;
-    }
-    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = base + (size_t)J * NB * p.v.np + (size_t)kb * NB;
-        ld = p.v.np;
-    }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const WarpCoord& wc) const {
+    __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_F, I * NB, kb * NB}; }
+    __device__ TileRef b_ref(const Params&, int kb) const { return TileRef{SRC_F, J * NB, kb * NB}; }
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
         double* C = base + (size_t)I * NB * p.v.np + (size_t)J * NB;
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
-                double2* q = reinterpret_cast<double2*>(C + (size_t)wc.row(mi) * p.v.np + wc.col(ni));
-                double2 c = *q;
-                c.x -= acc[mi][ni][0];
-                c.y -= acc[mi][ni][1];
-                *q = c;
+                double* q = C + (size_t)wc.row(mi) * p.v.np;
+                if (Coord::kPairs) {
+                    double2* q2 = reinterpret_cast<double2*>(q + wc.col(ni, 0));
+                    double2 c = *q2;
+                    c.x -= acc[mi][ni][0];
+                    c.y -= acc[mi][ni][1];
+                    *q2 = c;
+                } else {
+                    q[wc.col(ni, 0)] -= acc[mi][ni][0];
+                    q[wc.col(ni, 1)] -= acc[mi][ni][1];
+                }
             }
     }
 };
@@ -215,32 +435,23 @@ struct TrsmJob {
     struct Params { FactorView v; int jb; };
     int kb0, kb1, I;
     double* base;
-    const double* dl;
     __device__ bool init(const Params& p) {
         I = p.jb + 1 + blockIdx.x;
         if (I >= p.v.nb) return false;
         kb0 = p.jb;
         kb1 = p.jb + 1;
         base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
-        dl = p.v.DL + (size_t)blockIdx.y * p.v.dstride + (size_t)p.jb * NB * NB;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = base + (size_t)I * NB * p.v.np + (size_t)kb * NB;
-        ld = p.v.np;
-    }
-    __device__ void b_src(const Params&, int, const double*& ptr, int& ld) const {
-        ptr = dl;  // B[n=c][k] = Linv[c][k]
-        ld = NB;
-    }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const WarpCoord& wc) const {
+    __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_F, I * NB, kb * NB}; }
+    __device__ TileRef b_ref(const Params& p, int) const { return TileRef{SRC_DL, p.jb * NB, 0}; }   // B[n=c][k] = Linv[c][k]
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
         double* C = base + (size_t)I * NB * p.v.np + (size_t)p.jb * NB;
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-                *reinterpret_cast<double2*>(C + (size_t)wc.row(mi) * p.v.np + wc.col(ni)) =
-                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            for (int ni = 0; ni < 4; ++ni) store_pair(C, p.v.np, wc, mi, ni, acc[mi][ni][0], acc[mi][ni][1]);
     }
 };
 
@@ -248,6 +459,7 @@ struct TrsmJob {
 //   W[b:c, a:b] = -W[b:c,b:c] * L[b:c,a:b] * W[a:b,a:b], stored transposed in the upper triangle.
 //   G1:  Tt[j][k'] = sum_k U[j][k] L[k'][k]        (j in [a,b), k' in [b,c), k in [j,b))
 //   G2:  U[j][i]   = -sum_k' Tt[j][k'] U[k'][i]    (i in [b,c), k' in [b,i])
+// Scratch of merge m (blockIdx.z) at level s: rows [m s NB, (m+1) s NB) of an (s NB)-wide matrix.
 struct TrtriParams {
     FactorView v;
     double* T;        // batch base of the merge scratch
@@ -258,86 +470,67 @@ struct TrtriParams {
 struct TrtriG1Job {
     static constexpr bool kBNMajor = false;
     typedef TrtriParams Params;
-    int kb0, kb1, J, Kp, a, b;
-    double* base;
-    const double* du;
-    double* tt;
+    int kb0, kb1, J, Kp, a, b, jl, kl;
     __device__ bool init(const Params& p) {
         a = blockIdx.z * 2 * p.s;
         b = a + p.s;
         if (b >= p.v.nb) return false;
         const int c = min(a + 2 * p.s, p.v.nb);
-        const int jl = blockIdx.x / p.s, kl = blockIdx.x % p.s;
+        jl = blockIdx.x / p.s;
+        kl = blockIdx.x % p.s;
         J = a + jl;
         Kp = b + kl;
         if (Kp >= c) return false;
         kb0 = J;
         kb1 = b;
-        base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
-        du = p.v.DU + (size_t)blockIdx.y * p.v.dstride;
-        const size_t ldt = (size_t)p.s * NB;
-        tt = p.T + (size_t)blockIdx.y * p.tstride + (size_t)blockIdx.z * ldt * ldt + (size_t)jl * NB * ldt + (size_t)kl * NB;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        if (kb == J) { ptr = du + (size_t)J * NB * NB; ld = NB; }
-        else { ptr = base + (size_t)J * NB * p.v.np + (size_t)kb * NB; ld = p.v.np; }
+    __device__ TileRef a_ref(const Params&, int kb) const {
+        return kb == J ? TileRef{SRC_DU, J * NB, 0} : TileRef{SRC_F, J * NB, kb * NB};
     }
-    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = base + (size_t)Kp * NB * p.v.np + (size_t)kb * NB;
-        ld = p.v.np;
-    }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const WarpCoord& wc) const {
+    __device__ TileRef b_ref(const Params&, int kb) const { return TileRef{SRC_F, Kp * NB, kb * NB}; }
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
         const size_t ldt = (size_t)p.s * NB;
+        double* tt = p.T + (size_t)blockIdx.y * p.tstride + ((size_t)blockIdx.z * ldt + (size_t)jl * NB) * ldt + (size_t)kl * NB;
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-                *reinterpret_cast<double2*>(tt + (size_t)wc.row(mi) * ldt + wc.col(ni)) =
-                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            for (int ni = 0; ni < 4; ++ni) store_pair(tt, ldt, wc, mi, ni, acc[mi][ni][0], acc[mi][ni][1]);
     }
 };
 
 struct TrtriG2Job {
     static constexpr bool kBNMajor = true;
     typedef TrtriParams Params;
-    int kb0, kb1, J, I, a, b;
-    double* base;
-    const double* du;
-    const double* tt;  // row block J of the merge scratch
+    int kb0, kb1, J, I, a, b, jl;
     __device__ bool init(const Params& p) {
         a = blockIdx.z * 2 * p.s;
         b = a + p.s;
         if (b >= p.v.nb) return false;
         const int c = min(a + 2 * p.s, p.v.nb);
-        const int jl = blockIdx.x / p.s, il = blockIdx.x % p.s;
+        jl = blockIdx.x / p.s;
+        const int il = blockIdx.x % p.s;
         J = a + jl;
         I = b + il;
         if (I >= c) return false;
         kb0 = b;
         kb1 = I + 1;
-        base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
-        du = p.v.DU + (size_t)blockIdx.y * p.v.dstride;
-        const size_t ldt = (size_t)p.s * NB;
-        tt = p.T + (size_t)blockIdx.y * p.tstride + (size_t)blockIdx.z * ldt * ldt + (size_t)jl * NB * ldt;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = tt + (size_t)(kb - b) * NB;
-        ld = p.s * NB;
+    __device__ TileRef a_ref(const Params& p, int kb) const {
+        return TileRef{SRC_T, (int)blockIdx.z * p.s * NB + jl * NB, (kb - b) * NB};
     }
-    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        if (kb == I) { ptr = du + (size_t)I * NB * NB; ld = NB; }
-        else { ptr = base + (size_t)kb * NB * p.v.np + (size_t)I * NB; ld = p.v.np; }
+    __device__ TileRef b_ref(const Params&, int kb) const {   // N-major: rows = k', cols = i
+        return kb == I ? TileRef{SRC_DU, I * NB, 0} : TileRef{SRC_F, kb * NB, I * NB};
     }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const WarpCoord& wc) const {
-        double* C = base + (size_t)J * NB * p.v.np + (size_t)I * NB;
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
+        double* C = p.v.F + (size_t)blockIdx.y * p.v.fstride + (size_t)J * NB * p.v.np + (size_t)I * NB;
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-                *reinterpret_cast<double2*>(C + (size_t)wc.row(mi) * p.v.np + wc.col(ni)) =
-                    make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+            for (int ni = 0; ni < 4; ++ni) store_pair(C, p.v.np, wc, mi, ni, -acc[mi][ni][0], -acc[mi][ni][1]);
     }
 };
 

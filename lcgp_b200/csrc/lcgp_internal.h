@@ -7,11 +7,13 @@
 namespace lcgp {
 
 struct FactorView;
+struct GemmSrcs;
 
 // potrf.cu
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
                           int* info, int panel_width, cudaStream_t stream);
 size_t trtri_scratch_blocks(int nb);
+void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[]);
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);
 
 // Per-latent kernel hyper-parameters, device arrays of length q_loc (ell: q_loc x d).

@@ -7,7 +7,75 @@
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace lcgp {
+
+// ---- staging-engine selection and tensor-map encoding ---------------------------------------------
+bool gemm_use_tma() {
+    static const bool v = [] {
+        const char* e = std::getenv("LCGP_GEMM");
+        return !(e && std::strcmp(e, "cpasync") == 0);   // default: TMA engine
+    }();
+    return v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// 3-D map (column, row, batch) over a row-major fp64 buffer; box = 16 columns x box_rows rows, 128-byte swizzle
+static cudaError_t encode_map(CUtensorMap* m, const double* base, int cols, int rows, int batch, int ld,
+                              size_t bstride, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)bstride * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)TMA_BOX_K, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSRC], int batch) {
+    ctx.srcs = srcs;
+    ctx.tma = gemm_use_tma();
+    if (!ctx.tma) return cudaSuccess;
+    std::memset(&ctx.maps, 0, sizeof(ctx.maps));
+    for (int i = 0; i < NSRC; ++i) {
+        if (!srcs.base[i] || rows[i] <= 0) continue;
+        cudaError_t e = encode_map(&ctx.maps.km[i], srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB);
+        if (e != cudaSuccess) return e;
+        if (i == SRC_F || i == SRC_DU) {
+            e = encode_map(&ctx.maps.nm[i == SRC_F ? 0 : 1], srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i],
+                           srcs.bstride[i], BK);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+// sources every factor-based GEMM has: F, DU, DL
+void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[NSRC]) {
+    std::memset(&s, 0, sizeof(s));
+    for (int i = 0; i < NSRC; ++i) rows[i] = 0;
+    s.base[SRC_F] = v.F;   s.ld[SRC_F] = v.np;  s.bstride[SRC_F] = v.fstride;   rows[SRC_F] = v.np;
+    s.base[SRC_DU] = v.DU; s.ld[SRC_DU] = NB;   s.bstride[SRC_DU] = v.dstride;  rows[SRC_DU] = v.nb * NB;
+    s.base[SRC_DL] = v.DL; s.ld[SRC_DL] = NB;   s.bstride[SRC_DL] = v.dstride;  rows[SRC_DL] = v.nb * NB;
+}
 
 // ------------------------------------------------------------------------------------------
 // Diagonal-block kernel: one CTA (16 x 16 threads) per matrix; the 128 x 128 block is REGISTER
@@ -180,12 +248,19 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
     if (pw < 1) pw = 1;
+    GemmCtx ctx;
+    {
+        GemmSrcs srcs;
+        int rows[NSRC];
+        factor_srcs(v, srcs, rows);
+        if ((e = gemm_make_ctx(ctx, srcs, rows, batch)) != cudaSuccess) return e;
+    }
     for (int j0 = 0; j0 < v.nb; j0 += pw) {
         const int j1 = (j0 + pw < v.nb) ? j0 + pw : v.nb;
         for (int j = j0; j < j1; ++j) {
             if (j > j0) {
                 SyrkJob::Params cp{v, j0, j, 0, j};
-                e = gemm_launch<SyrkJob>(cp, dim3(v.nb - j, batch, 1), stream);
+                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), stream);
                 if (e != cudaSuccess) return e;
             }
             potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, stream>>>(v, DLw, DUw, j, logdet_part, info);
@@ -194,14 +269,14 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
             const int T = v.nb - j - 1;
             if (T > 0) {
                 TrsmJob::Params tp{v, j};
-                e = gemm_launch<TrsmJob>(tp, dim3(T, batch, 1), stream);
+                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), stream);
                 if (e != cudaSuccess) return e;
             }
         }
         const int T = v.nb - j1;
         if (T > 0) {
             SyrkJob::Params sp{v, j0, j1, j1, -1};
-            e = gemm_launch<SyrkJob>(sp, dim3(T * (T + 1) / 2, batch, 1), stream);
+            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T * (T + 1) / 2, batch, 1), stream);
             if (e != cudaSuccess) return e;
         }
     }
@@ -219,13 +294,20 @@ size_t trtri_scratch_blocks(int nb) {
 }
 
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream) {
+    GemmSrcs srcs;
+    int rows[NSRC];
+    factor_srcs(v, srcs, rows);
     for (int s = 1; s < v.nb; s *= 2) {
         const int merges = (v.nb + 2 * s - 1) / (2 * s);
+        srcs.base[SRC_T] = scratch; srcs.ld[SRC_T] = s * NB; srcs.bstride[SRC_T] = tstride; rows[SRC_T] = merges * s * NB;
+        GemmCtx ctx;
+        cudaError_t e = gemm_make_ctx(ctx, srcs, rows, batch);
+        if (e != cudaSuccess) return e;
         TrtriParams p{v, scratch, tstride, s};
         dim3 grid(s * s, batch, merges);
-        cudaError_t e = gemm_launch<TrtriG1Job>(p, grid, stream);
+        e = gemm_launch<TrtriG1Job>(ctx, p, grid, stream);
         if (e != cudaSuccess) return e;
-        e = gemm_launch<TrtriG2Job>(p, grid, stream);
+        e = gemm_launch<TrtriG2Job>(ctx, p, grid, stream);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

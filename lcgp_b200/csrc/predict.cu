@@ -23,28 +23,19 @@ struct PredictJob {
     static constexpr bool kBNMajor = true;
     typedef PredictParams Params;
     int kb0, kb1, Tb, Ib;
-    const double* base;
-    const double* du;
-    const double* crow;
     __device__ bool init(const Params& p) {
         Tb = blockIdx.x / p.v.nb;
         Ib = blockIdx.x % p.v.nb;
         kb0 = 0;
         kb1 = Ib + 1;
-        base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
-        du = p.v.DU + (size_t)blockIdx.y * p.v.dstride;
-        crow = p.c0s + (size_t)blockIdx.y * p.cstride + (size_t)Tb * NB * p.v.np;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        ptr = crow + (size_t)kb * NB;
-        ld = p.v.np;
+    __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_C, Tb * NB, kb * NB}; }
+    __device__ TileRef b_ref(const Params&, int kb) const {   // N-major: rows = k, cols = i
+        return kb == Ib ? TileRef{SRC_DU, Ib * NB, 0} : TileRef{SRC_F, kb * NB, Ib * NB};
     }
-    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        if (kb == Ib) { ptr = du + (size_t)Ib * NB * NB; ld = NB; }
-        else { ptr = base + (size_t)kb * NB * p.v.np + (size_t)Ib * NB; ld = p.v.np; }
-    }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double* smem, const WarpCoord& wc) const {
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double* smem, const Coord& wc) const {
         double* rs = smem;  // [NB][4]
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) {
@@ -98,7 +89,15 @@ cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, 
                                        q_loc, cstride, stream);
     if (e != cudaSuccess) return e;
     PredictParams p{v, c0s, cstride, part, n0p};
-    e = gemm_launch<PredictJob>(p, dim3((n0p / NB) * v.nb, q_loc, 1), stream);
+    GemmCtx ctx;
+    {
+        GemmSrcs srcs;
+        int rows[NSRC];
+        factor_srcs(v, srcs, rows);
+        srcs.base[SRC_C] = c0s; srcs.ld[SRC_C] = v.np; srcs.bstride[SRC_C] = cstride; rows[SRC_C] = n0p;
+        if ((e = gemm_make_ctx(ctx, srcs, rows, q_loc)) != cudaSuccess) return e;
+    }
+    e = gemm_launch<PredictJob>(ctx, p, dim3((n0p / NB) * v.nb, q_loc, 1), stream);
     if (e != cudaSuccess) return e;
     predict_finish_kernel<<<dim3((n0 + 7) / 8, q_loc), 256, 0, stream>>>(v.np, v.nb, n0, n0p, c0s, cstride, atil, part,
                                                                           kp.s0, kp.D, ghat, gvar);

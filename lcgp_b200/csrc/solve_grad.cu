@@ -140,26 +140,21 @@ struct ContractJob {
     static constexpr bool kBNMajor = false;
     typedef ContractParams Params;
     int kb0, kb1, I, J;
-    const double* base;
-    const double* du;
     __device__ bool init(const Params& p) {
         if ((int)blockIdx.x >= p.ntiles) return false;
         tri_decode(blockIdx.x, I, J);
         kb0 = I;
         kb1 = p.v.nb;
-        base = p.v.F + (size_t)blockIdx.y * p.v.fstride;
-        du = p.v.DU + (size_t)blockIdx.y * p.v.dstride;
         return true;
     }
-    __device__ void a_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        if (kb == I) { ptr = du + (size_t)I * NB * NB; ld = NB; }
-        else { ptr = base + (size_t)I * NB * p.v.np + (size_t)kb * NB; ld = p.v.np; }
+    __device__ TileRef a_ref(const Params&, int kb) const {
+        return kb == I ? TileRef{SRC_DU, I * NB, 0} : TileRef{SRC_F, I * NB, kb * NB};
     }
-    __device__ void b_src(const Params& p, int kb, const double*& ptr, int& ld) const {
-        if (kb == J) { ptr = du + (size_t)J * NB * NB; ld = NB; }
-        else { ptr = base + (size_t)J * NB * p.v.np + (size_t)kb * NB; ld = p.v.np; }
+    __device__ TileRef b_ref(const Params&, int kb) const {
+        return kb == J ? TileRef{SRC_DU, J * NB, 0} : TileRef{SRC_F, J * NB, kb * NB};
     }
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double* smem, const WarpCoord& wc) const {
+    template <class Coord>
+    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double* smem, const Coord& wc) const {
         const int d = p.d, n = p.n, k = blockIdx.y, tid = threadIdx.x;
         double* xi = smem;                 // [d][NB]   x_i / ell
         double* xj = xi + d * NB;          // [d][NB]
@@ -186,7 +181,9 @@ struct ContractJob {
         __syncthreads();
         const double s0 = p.kp.s0[k], lnug = p.kp.lnug[k], dk = p.kp.D[k];
         const double nu = lnug / (1.0 + lnug);
-        const int cbase = wc.wn * 32 + 2 * wc.t;  // + ni*8 + e
+        int cc[8];                          // this lane's 8 tile columns: (ni, e) -> cc[2 ni + e]
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { cc[2 * ni] = wc.col(ni, 0); cc[2 * ni + 1] = wc.col(ni, 1); }
         double acc_s0 = 0.0, acc_nug = 0.0;
         // pass 1: C0 per element; acc <- G * C0
 #pragma unroll
@@ -198,13 +195,10 @@ struct ContractJob {
             for (int m = 0; m < d; ++m) {
                 const double a = xi[m * NB + r];
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const double2 b = *reinterpret_cast<const double2*>(xj + m * NB + cbase + ni * 8);
-                    const double S0 = fabs(a - b.x), S1 = fabs(a - b.y);
-                    P[2 * ni] *= (1.0 + S0);
-                    V[2 * ni] -= S0;
-                    P[2 * ni + 1] *= (1.0 + S1);
-                    V[2 * ni + 1] -= S1;
+                for (int e = 0; e < 8; ++e) {
+                    const double S = fabs(a - xj[m * NB + cc[e]]);
+                    P[e] *= (1.0 + S);
+                    V[e] -= S;
                 }
             }
             const double dsr = dk * sri[r], al = ai[r];
@@ -213,7 +207,7 @@ struct ContractJob {
             for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int c = cbase + ni * 8 + e;
+                    const int c = cc[2 * ni + e];
                     const double c0 = P[2 * ni + e] * exp(V[2 * ni + e]);
                     const double G = dsr * srj[c] * acc[mi][ni][e] - al * aj[c];
                     const double delta = (gi == J * NB + c) ? 1.0 : 0.0;
@@ -228,18 +222,17 @@ struct ContractJob {
         if (lane == 0) { red[0 * 8 + warp] = acc_s0; red[1 * 8 + warp] = acc_nug; }
         // pass 2: sum_ij (G C0)_ij S_m^2 / (1 + S_m) per input dimension m
         for (int m = 0; m < d; ++m) {
-            double a[8];
-            double2 b[4];
+            double a[8], b[8];
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi) a[mi] = xi[m * NB + wc.row(mi)];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double2*>(xj + m * NB + cbase + ni * 8);
+            for (int e = 0; e < 8; ++e) b[e] = xj[m * NB + cc[e]];
             double sum = 0.0;
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
-                    const double S0 = fabs(a[mi] - b[ni].x), S1 = fabs(a[mi] - b[ni].y);
+                    const double S0 = fabs(a[mi] - b[2 * ni]), S1 = fabs(a[mi] - b[2 * ni + 1]);
                     sum = fma(acc[mi][ni][0] * S0, S0 * rcp_ge1(1.0 + S0), sum);
                     sum = fma(acc[mi][ni][1] * S1, S1 * rcp_ge1(1.0 + S1), sum);
                 }
@@ -278,8 +271,16 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
                           cudaStream_t stream) {
     const int ntiles = v.nb * (v.nb + 1) / 2;
     ContractParams p{v, a.n, a.d, a.X, a.sr, a.alpha, a.kp, tile_part, ntiles};
+    GemmCtx ctx;
+    {
+        GemmSrcs srcs;
+        int rows[NSRC];
+        factor_srcs(v, srcs, rows);
+        cudaError_t e0 = gemm_make_ctx(ctx, srcs, rows, a.q_loc);
+        if (e0 != cudaSuccess) return e0;
+    }
     if (ev_before) cudaEventRecord(ev_before, stream);
-    cudaError_t e = gemm_launch<ContractJob>(p, dim3(ntiles, a.q_loc, 1), stream);
+    cudaError_t e = gemm_launch<ContractJob>(ctx, p, dim3(ntiles, a.q_loc, 1), stream);
     if (ev_after) cudaEventRecord(ev_after, stream);
     if (e != cudaSuccess) return e;
     contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
