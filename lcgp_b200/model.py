@@ -495,9 +495,13 @@ class LCGP:
                 self.lsigma2s.unconstrained]
 
     def _get_param_graph(self):
-        reps = torch.as_tensor(self.diag_error_structure, dtype=torch.long)
-        return (self.lLmb.value(), self.lLmb0.value(),
-                torch.repeat_interleave(self.lsigma2s.value(), reps), self.lnugGPs.value())
+        idx = getattr(self, '_err_index', None)
+        if idx is None or idx.numel() != int(self.p):
+            # output j -> its error group (get_param's expansion, lcgp.py:521-530), built once:
+            # torch.repeat_interleave with a repeats tensor costs ~1 ms per call
+            reps = torch.as_tensor(self.diag_error_structure, dtype=torch.long)
+            idx = self._err_index = torch.repeat_interleave(torch.arange(len(self.diag_error_structure)), reps)
+        return (self.lLmb.value(), self.lLmb0.value(), self.lsigma2s.value()[idx], self.lnugGPs.value())
 
     def get_param(self):
         """lcgp.py:515-532: (lLmb, lLmb0, lsigma2s expanded to a p-vector, lnugGPs), detached."""
