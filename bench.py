@@ -328,7 +328,7 @@ def run_ours(args):
             'gpu_launches': eng.launches_per_eval * args.steps,
             # dominant kernel: the fused A^-1 / gradient-contraction GEMM, one launch per step (largest
             # single kernel, ~1/3 of the step); timed live with CUDA events recorded around the launch
-            'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel<ContractJob> (A^-1 = U U^T tiles on DMMA + fused gradient contraction)',
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_tma_kernel<ContractJob> (A^-1 = U U^T tiles: TMA-staged DMMA GEMM + fused gradient contraction)',
                          'achieved': tf(stages[4]), 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(stages[4]) / fp64_peak,
                          'peak_source': 'cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
                          'flops_per_launch': stage_flops, 'kernel_ms': float(stages[4]), 'traffic': traffic},
