@@ -233,6 +233,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))   # N ranks preprocess concurrently on one host
     from lcgp_b200 import _cabi
 
     model, t_ctor, (x, y, mk) = build_model(args.config)

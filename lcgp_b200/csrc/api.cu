@@ -10,7 +10,8 @@
 namespace lcgp {
 
 // ---- tunables (environment, read once) --------------------------------------------------------
-//   LCGP_PANEL_W  : block columns per Cholesky panel (K = 128 * W in the trailing update); default 8
+//   LCGP_PANEL_W  : block columns per Cholesky panel (K = 128 * W in the trailing update); default: 16 for
+//                   groups of >= 8 latents, else 8
 //   LCGP_STREAMS  : independent groups of latents factored on separate streams so that one group's
 //                   serial panel work overlaps another group's trailing updates; default min(4, q_loc)
 static int env_int(const char* name, int dflt, int lo, int hi) {
@@ -19,7 +20,7 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     int v = std::atoi(e);
     return v < lo ? lo : (v > hi ? hi : v);
 }
-static int panel_width() { static const int v = env_int("LCGP_PANEL_W", 8, 1, 16); return v; }
+static int panel_width() { static const int v = env_int("LCGP_PANEL_W", 0, 0, 16); return v; }   // 0 = auto
 constexpr int MAX_GROUPS = 4;
 static int stream_groups(int q) {
     static const int v = env_int("LCGP_STREAMS", MAX_GROUPS, 1, MAX_GROUPS);

@@ -337,30 +337,36 @@ struct GemmCtx {
     GemmSrcs srcs;
     GemmMaps maps;
     bool tma;        // maps are valid and the TMA engine is selected
+    int device;      // current device (the opt-in shared-memory attribute is per device)
 };
+constexpr int MAX_DEVICES = 64;
 
 bool gemm_use_tma();   // engine selection (env LCGP_GEMM=tma|cpasync), defined in potrf.cu
+int gemm_tma_min_kblocks();   // launches whose longest K run is shorter use the cp.async engine (env LCGP_TMA_MIN_KB)
 // Fills ctx.srcs from the arguments and, when the TMA engine is selected, encodes the tensor maps.
 // rows[] = rows per batch element of each source (0 = source unused).
 cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSRC], int batch);
 
+// max_kblocks: length (in 128-blocks) of the longest K run any tile of this launch has
 template <class Job>
-inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p, dim3 grid, cudaStream_t stream) {
-    if (ctx.tma) {
-        static bool configured = false;
-        if (!configured) {
+inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p, dim3 grid, cudaStream_t stream,
+                               int max_kblocks = 1 << 20) {
+    const int dev = (ctx.device >= 0 && ctx.device < MAX_DEVICES) ? ctx.device : 0;
+    if (ctx.tma && max_kblocks >= gemm_tma_min_kblocks()) {
+        static bool configured[MAX_DEVICES] = {};
+        if (!configured[dev]) {
             cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_TMA);
             if (e != cudaSuccess) return e;
-            configured = true;
+            configured[dev] = true;
         }
         gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
     } else {
         constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[MAX_DEVICES] = {};
+        if (!configured[dev]) {
             cudaError_t e = cudaFuncSetAttribute(gemm_dmma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured = true;
+            configured[dev] = true;
         }
         gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p, ctx.srcs);
     }

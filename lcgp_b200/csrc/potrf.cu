@@ -21,6 +21,14 @@ bool gemm_use_tma() {
     return v;
 }
 
+int gemm_tma_min_kblocks() {
+    static const int v = [] {
+        const char* e = std::getenv("LCGP_TMA_MIN_KB");
+        return (e && *e) ? std::atoi(e) : 1;
+    }();
+    return v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -53,6 +61,8 @@ static cudaError_t encode_map(CUtensorMap* m, const double* base, int cols, int 
 cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSRC], int batch) {
     ctx.srcs = srcs;
     ctx.tma = gemm_use_tma();
+    ctx.device = 0;
+    cudaGetDevice(&ctx.device);
     if (!ctx.tma) return cudaSuccess;
     std::memset(&ctx.maps, 0, sizeof(ctx.maps));
     for (int i = 0; i < NSRC; ++i) {
@@ -231,10 +241,13 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
 }
 
 static cudaError_t diag_configure() {
-    static bool done = false;
-    if (done) return cudaSuccess;
+    static bool done[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEVICES) dev = 0;
+    if (done[dev]) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
-    if (e == cudaSuccess) done = true;
+    if (e == cudaSuccess) done[dev] = true;
     return e;
 }
 
@@ -247,7 +260,7 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
                           int* info, int pw, cudaStream_t stream) {
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
-    if (pw < 1) pw = 1;
+    if (pw < 1) pw = batch >= 8 ? 16 : 8;   // auto: wide panels pay once the batch alone fills the SMs
     GemmCtx ctx;
     {
         GemmSrcs srcs;
@@ -260,7 +273,7 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
         for (int j = j0; j < j1; ++j) {
             if (j > j0) {
                 SyrkJob::Params cp{v, j0, j, 0, j};
-                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), stream);
+                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), stream, j - j0);
                 if (e != cudaSuccess) return e;
             }
             potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, stream>>>(v, DLw, DUw, j, logdet_part, info);
@@ -269,14 +282,14 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
             const int T = v.nb - j - 1;
             if (T > 0) {
                 TrsmJob::Params tp{v, j};
-                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), stream);
+                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), stream, 1);
                 if (e != cudaSuccess) return e;
             }
         }
         const int T = v.nb - j1;
         if (T > 0) {
             SyrkJob::Params sp{v, j0, j1, j1, -1};
-            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T * (T + 1) / 2, batch, 1), stream);
+            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T * (T + 1) / 2, batch, 1), stream, j1 - j0);
             if (e != cudaSuccess) return e;
         }
     }
@@ -305,9 +318,9 @@ cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, 
         if (e != cudaSuccess) return e;
         TrtriParams p{v, scratch, tstride, s};
         dim3 grid(s * s, batch, merges);
-        e = gemm_launch<TrtriG1Job>(ctx, p, grid, stream);
+        e = gemm_launch<TrtriG1Job>(ctx, p, grid, stream, s);
         if (e != cudaSuccess) return e;
-        e = gemm_launch<TrtriG2Job>(ctx, p, grid, stream);
+        e = gemm_launch<TrtriG2Job>(ctx, p, grid, stream, s);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

@@ -114,8 +114,12 @@ class CudaEngine:
         """Kernel launches of one objective+gradient evaluation (mirrors csrc/api.cu / potrf.cu)."""
         import os
         nb = _cabi.padded(self.n) // _cabi.NB
-        pw = min(max(int(os.environ.get('LCGP_PANEL_W', '8') or 8), 1), 16)
         groups = min(self.q_loc, min(max(int(os.environ.get('LCGP_STREAMS', '4') or 4), 1), 4))
+        if getattr(self, 'group_flags', 0):
+            groups = min(self.q_loc, (self.group_flags >> 4) & 15)
+        pw = int(os.environ.get('LCGP_PANEL_W', '0') or 0)
+        if pw <= 0:
+            pw = 16 if (self.q_loc + groups - 1) // groups >= 8 else 8     # auto rule of csrc/potrf.cu
         potrf = 0
         for j0 in range(0, nb, pw):
             j1 = min(j0 + pw, nb)
