@@ -302,6 +302,21 @@ def run_ours(args):
         torch.distributed.all_reduce(t_dev, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(st, op=torch.distributed.ReduceOp.MAX)
+    # ---- prediction (a7): latent means / variances at 1024 test points from the factor in the workspace
+    n0 = 1024
+    x0 = torch.as_tensor(np.random.default_rng(7).uniform(0, 1, (n0, d)))
+    x0 = x0 * (model.x_max - model.x_min) + model.x_min
+    model.predict(x0)                        # includes the aux refresh
+    barrier()
+    w0 = time.perf_counter()
+    model.predict(x0)
+    torch.cuda.synchronize()
+    t_pred = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_pred, op=torch.distributed.ReduceOp.MAX)
+    pred = {'n0': n0, 'wall_ms': float(t_pred) * 1e3, 'points_per_s': n0 / float(t_pred),
+            'tflops': q * float(n0) * n * n / float(t_pred) / 1e12,
+            'note': 'LCGP.predict() end to end (host x0 in, p x n0 host tensors out); flop = q n0 n^2'}
     clk = clocks.stop() if rank == 0 else None
     t_dev, t_e2e, stages = float(t_dev), float(t_e2e), st.cpu().numpy()
 
@@ -358,6 +373,7 @@ def run_ours(args):
                                         'sample': f'failed: {ex!r}'}
         else:
             line['cpu_baseline'] = None
+        line['predict'] = pred
         if world == 1 and not args.no_fit:
             line['fit'] = fit_wall(args.fit_config, not args.no_cpu_baseline)
         print(json.dumps(line))
