@@ -403,3 +403,24 @@ def test_nan_input_is_reported_not_silently_used():
     m.lLmb0.unconstrained.data[0] = float('nan')
     with pytest.raises(RuntimeError, match='Cholesky failed'):
         m.loss()
+
+
+# ---------------------------------------------------------------- parity at BASELINE's full matrix size
+def test_parity_at_config4_matrix_size():
+    """n = 8000 unique inputs, d = 10 (config 4's matrix size, 63 blocks, 2 latents, small p so that the
+    oracle's autograd through two 8000 x 8000 Choleskys stays within a minute and ~30 GB of host memory)."""
+    import psutil
+    if psutil.virtual_memory().available < 60e9:
+        pytest.skip('needs ~30 GB of host memory for the oracle autograd graph')
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y, x0, _ = synthetic.latent_mixture(n=8000, d=10, p=8, q_true=4, seed=8000, rep_choices=(1, 2, 3), n0=16)
+    m = LCGP(y=y, x=x, q=2, submethod='rep')
+    o = O.LCGPOracle(y=y, x=x, q=2, submethod='rep', skip_xnorm=True)
+    assert int(m.n) == 8000
+    f, g = m.loss_and_grad()
+    fo, go = o.loss_and_grad()
+    assert abs(f - fo) <= NLL_TOL * abs(fo), (f, fo)
+    assert np.max(np.abs(g - go)) <= GRAD_TOL * np.max(np.abs(go))
+    yp, ypv, ycv = m.predict(x0)
+    ypo, ypvo, ycvo = o.predict(torch.as_tensor(x0))
+    assert rel(yp, ypo) < PRED_TOL and rel(ypv, ypvo) < PRED_TOL and rel(ycv, ycvo) < PRED_TOL
