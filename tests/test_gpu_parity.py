@@ -424,3 +424,30 @@ def test_parity_at_config4_matrix_size():
     yp, ypv, ycv = m.predict(x0)
     ypo, ypvo, ycvo = o.predict(torch.as_tensor(x0))
     assert rel(yp, ypo) < PRED_TOL and rel(ypv, ypvo) < PRED_TOL and rel(ycv, ycvo) < PRED_TOL
+
+
+def test_workspace_guard_bands_untouched():
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with guard bands:
+    the caller-owned workspace and the prediction scratch sit inside larger buffers filled with a
+    sentinel; after objective+gradient and predict the bands must be intact (both staging engines write
+    only inside the sizes lcgp_workspace_bytes / lcgp_predict_scratch_bytes report)."""
+    x, y, xu = make_ragged_rep_data(seed=12, n_unique=300, p=5, d=3)
+    m = LCGP(y=y, x=x, q=3, submethod='rep')
+    eng = m.engine
+    guard = 4096
+    sentinel = 12345.6789
+    nws = eng.ws_bytes // 8
+    big = torch.full((nws + 2 * guard,), sentinel, dtype=DT, device=eng.device)
+    eng.ws = big[guard:guard + nws]
+    f, g = m.loss_and_grad()
+    need = int(eng.lib.lcgp_predict_scratch_bytes(eng.n, eng.q_loc, 200)) // 8
+    bigs = torch.full((need + 2 * guard,), sentinel, dtype=DT, device=eng.device)
+    eng._scratch = bigs[guard:guard + need]
+    out = m.predict(np.random.default_rng(0).uniform(0, 1, (200, 3)))
+    torch.cuda.synchronize()
+    for buf, n_in in ((big, nws), (bigs, need)):
+        assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n_in:] == sentinel).all())
+    o = O.LCGPOracle(y=y, x=x, q=3, submethod='rep')
+    fo, go = o.loss_and_grad()
+    assert abs(f - fo) <= NLL_TOL * abs(fo) and np.max(np.abs(g - go)) <= GRAD_TOL * np.max(np.abs(go))
+    assert torch.isfinite(out[0]).all()
