@@ -296,7 +296,7 @@ class LCGP:
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             self._world = torch.distributed.get_world_size()
             self._rank = torch.distributed.get_rank()
-        self._local_idx = torch.arange(self._rank, self.q, self._world)
+        self._local_idx = torch.arange(self.q)[self._rank::self._world]   # empty when this rank owns no latent
 
         self._invalidate_aux()
         self.ghat = None

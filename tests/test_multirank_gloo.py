@@ -38,19 +38,20 @@ def _worker(rank, world, port, q, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('q', [3, 1])
-def test_sharded_objective_gradient_predict_fit(q):
+@pytest.mark.parametrize('q,world', [(3, 2), (1, 2), (1, 3)])     # (1, 3): a rank index beyond q owns nothing
+def test_sharded_objective_gradient_predict_fit(q, world):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from helpers import make_ragged_rep_data, move_params
     from oracle.lcgp_oracle import LCGPOracle
     from test_oracle_selfcheck import _Shim
-    world = 2
     port = 29500 + (os.getpid() % 2000)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, q, ret), nprocs=world, join=True)
     r0, r1 = ret[0], ret[1]
-    assert r0['local'] == list(range(0, q, 2)) and r1['local'] == list(range(1, q, 2))   # q=1: rank 1 owns nothing
+    for rk in range(world):                     # round-robin ownership; ranks >= q own nothing
+        assert ret[rk]['local'] == list(range(q))[rk::world]
+        assert ret[rk]['f'] == r0['f'] and np.array_equal(ret[rk]['fitted'], r0['fitted'])
     # every rank holds identical (all-reduced) values -> replicated host optimizer stays in lock-step
     assert r0['f'] == r1['f'] and np.array_equal(r0['g'], r1['g'])
     assert np.array_equal(r0['fitted'], r1['fitted'])
