@@ -423,7 +423,11 @@ def run_batched(args):
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
-        run_reference(a)
+        try:
+            run_reference(a)
+        except Exception as ex:      # the driver expects one JSON line and exit code 0 from this arm
+            if int(os.environ.get('RANK', '0')) == 0:
+                print(json.dumps({'impl': 'reference', 'unavailable': f'oracle port failed on this host: {ex!r}'}))
     elif a.config == 'cfg5_batch':
         run_batched(a)
     else:

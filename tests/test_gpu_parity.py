@@ -245,27 +245,56 @@ def test_fullcov_and_rep_fullcov_none():       # test_coverage_gaps.py:169-232
 # ---------------------------------------------------------------- a10: fit
 @pytest.mark.parametrize('optimizer', ['L-BFGS-B', 'torch-lbfgs'])
 def test_fit_matches_oracle_under_shared_optimizer(optimizer):
-    """Oracle and CUDA path under ONE optimizer, start and tolerance setting (SURVEY 7 'hard parts')."""
+    """Oracle and CUDA path under ONE optimizer, start and iteration budget (SURVEY 7 'hard parts').
+    L-BFGS amplifies the ~1e-16 differences between the two implementations by roughly 10^3 per 20
+    iterations on these weakly identified objectives (tools/fit_parity_probe.py: 1e-12 after 10
+    iterations, 1e-9 after 30, divergent trajectories after several hundred), so the north-star 1e-6 on
+    fitted hyper-parameters is asserted for a bounded budget; parity along the whole path is covered by
+    test_parity_along_fit_path, converged fits by the notebook test below."""
     x, y, xu = make_ragged_rep_data(seed=9, n_unique=80, p=4, d=2)
     m, o = _pair(x, y, q=3, submethod='rep')
     l0 = float(m.loss())
     if optimizer == 'L-BFGS-B':
-        m.fit(optimizer=optimizer, maxiter=60, ftol=1e-14, gtol=1e-9)
-        o.fit(method='L-BFGS-B', maxiter=60, ftol=1e-14, gtol=1e-9)
+        m.fit(optimizer=optimizer, maxiter=30)
+        o.fit(method='L-BFGS-B', maxiter=30)
+        assert m.n_evals - 1 == o.opt_result.nfev          # same number of closure calls (+1 for l0 above)
     else:
-        m.fit(optimizer=optimizer, max_iter=40)
-        o.fit(method='torch-lbfgs', max_iter=40)
+        m.fit(optimizer=optimizer, max_iter=20)
+        o.fit(method='torch-lbfgs', max_iter=20)
     l1, lo1 = float(m.loss()), float(o.loss().detach())
     assert l1 <= l0 + 1e-3                                       # test_rep.py:161-171
-    assert abs(l1 - lo1) <= 1e-8 * abs(lo1)
+    assert abs(l1 - lo1) <= 1e-9 * abs(lo1)
+    for a, b in ((m.lLmb, o.lLmb), (m.lLmb0, o.lLmb0), (m.lsigma2s, o.lsigma2s), (m.lnugGPs, o.lnugGPs)):
+        assert rel(a.numpy(), b.detach().numpy()) < PRED_TOL     # 1e-6, all four parameter blocks
     x0 = np.random.default_rng(5).uniform(0, 1, (25, 2))
     for a, b in zip(m.predict(x0), o.predict(torch.as_tensor(x0))):
-        assert rel(a, b) < 1e-5
-    # identifiable blocks agree tightly; lLmb0 / nugget sit on a flat ridge (SURVEY B-16) -> looser
-    assert rel(m.lLmb.numpy(), o.lLmb.detach().numpy()) < 1e-4
-    assert rel(m.lsigma2s.numpy(), o.lsigma2s.detach().numpy()) < 1e-4
+        assert rel(a, b) < PRED_TOL
     for t in m.get_param():
         assert torch.isfinite(t).all()
+
+
+def test_parity_along_fit_path():
+    """Objective and gradient parity at the iterates of a full CUDA-path fit (not only at init)."""
+    x, y, _ = synthetic.rep3d()
+    m, o = _pair(x, y, q=3, submethod='rep')
+    path = []
+    orig = m.loss_and_grad
+
+    def spy():
+        path.append(m._flat_get())
+        return orig()
+    m.loss_and_grad = spy
+    m.fit(maxiter=120)
+    m.loss_and_grad = orig
+    assert len(path) > 30
+    for v in [path[i] for i in np.linspace(0, len(path) - 1, 8).astype(int)]:
+        m._flat_set(v); o._flat_set(v)
+        f, g = m.loss_and_grad()
+        fo, go = o.loss_and_grad()
+        assert abs(f - fo) <= NLL_TOL * abs(fo)
+        # near the optimum the gradient is a ~1e-4 residue of cancelling O(1) terms (absolute difference
+        # measured there: 5e-12): relative 1e-8, with an absolute floor at the objective's own tolerance
+        assert np.max(np.abs(g - go)) <= max(GRAD_TOL * np.max(np.abs(go)), NLL_TOL * max(1.0, abs(fo)))
 
 
 def test_notebook_goldens_through_cuda_path():
@@ -277,6 +306,12 @@ def test_notebook_goldens_through_cuda_path():
     m.fit()
     np.testing.assert_allclose(m.lLmb.numpy().ravel(), GOLD['fitted_lengthscales'], rtol=1e-3)
     np.testing.assert_allclose(m.lsigma2s.numpy(), GOLD['fitted_lsigma2s'], rtol=1e-3)
+    # converged fit vs the oracle's converged fit (same SciPy defaults, 72 evaluations each): the
+    # identifiable blocks agree to 1e-5 (measured 2e-6 / 5e-8); see test_fit_matches_oracle_... for why not tighter
+    o = O.LCGPOracle(y=ytr, x=xtr, q=3, submethod='rep', diag_error_structure=[1, 1, 1], robust_mean=True)
+    o.fit()
+    assert rel(m.lLmb.numpy(), o.lLmb.detach().numpy()) < 1e-5 and rel(m.lsigma2s.numpy(), o.lsigma2s.detach().numpy()) < 1e-5
+    assert abs(float(m.loss()) - float(o.loss().detach())) <= 1e-9 * abs(float(o.loss().detach()))
     yp, ypv, ycv = (t.numpy() for t in m.predict(xte))
     assert round(float(evaluation.rmse(ytrue, yp)), 4) == GOLD['rmse']
     assert round(float(evaluation.normalized_rmse(ytrue, yp)), 4) == GOLD['nrmse']
@@ -424,6 +459,14 @@ def test_parity_at_config4_matrix_size():
     yp, ypv, ycv = m.predict(x0)
     ypo, ypvo, ycvo = o.predict(torch.as_tensor(x0))
     assert rel(yp, ypo) < PRED_TOL and rel(ypv, ypvo) < PRED_TOL and rel(ycv, ycvo) < PRED_TOL
+    # a point like the end of a fit: large kernel variance, nugget at its lower bound, short length-scales
+    lL = m.lLmb.numpy() * 0.35
+    m.lLmb.assign(lL); m.lLmb0.assign([25.0, 40.0]); m.lnugGPs.assign([1.2e-7, 1.2e-7]); m.lsigma2s.assign(m.lsigma2s.numpy() - 3.0)
+    o.set_constrained(lL, [25.0, 40.0], m.lsigma2s.numpy(), [1.2e-7, 1.2e-7])
+    f, g = m.loss_and_grad()
+    fo, go = o.loss_and_grad()
+    assert abs(f - fo) <= NLL_TOL * abs(fo), (f, fo)
+    assert np.max(np.abs(g - go)) <= GRAD_TOL * np.max(np.abs(go))
 
 
 def test_workspace_guard_bands_untouched():
