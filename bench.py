@@ -268,10 +268,12 @@ def run_ours(args):
     # ---- value: device-resident steps, CUDA events on the launching stream ----
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = int(_cabi.lib().lcgp_launch_count())
     e0.record()
     for s in range(args.steps):
         device_step()
     e1.record()
+    launches = int(_cabi.lib().lcgp_launch_count()) - launches0      # counted by the library at each launch site
     barrier()
     t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
 
@@ -341,7 +343,7 @@ def run_ours(args):
             'config': dict(workload_desc(args.config, model), parallelism=f'latents sharded over {world} rank(s)'),
             'e2e': {'value': args.steps / t_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': eng.h2d_bytes,
                     'd2h_bytes_per_step': eng.d2h_bytes if world == 1 else (1 + p + q * d + 2 * q) * 8},
-            'gpu_launches': eng.launches_per_eval * args.steps,
+            'gpu_launches': launches,
             # dominant kernel: the fused A^-1 / gradient-contraction GEMM, one launch per step (largest
             # single kernel, ~1/3 of the step); timed live with CUDA events recorded around the launch
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_tma_kernel<ContractJob> (A^-1 = U U^T tiles: TMA-staged DMMA GEMM + fused gradient contraction)',

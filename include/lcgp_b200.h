@@ -33,6 +33,9 @@ extern "C" {
 #define LCGP_E_DIM (-2)        /* d > LCGP_MAX_D or np not a multiple of LCGP_NB */
 #define LCGP_E_WORKSPACE (-3)  /* workspace too small */
 
+#define LCGP_FLAG_GRAD 1            /* lcgp_nll_grad flags bit0 */
+#define LCGP_FLAG_NO_LOOKAHEAD 256  /* bit8: keep each group's whole Cholesky on one stream */
+
 /* Constant data of one rank's share of an emulator (all device pointers).
  * rep mode (lcgp.py:554-630):  X = x_unique_s, sr = sqrt(r), YR = ybar_s * r (or ybar * r),
  *   w_j = sum_i r_i ybar_ji^2, t = ybar_std (or ones), scale = 1/n, sum_log_r = sum_i log r_i
@@ -75,7 +78,9 @@ size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
  * the p-vector of get_param (lcgp.py:515-532).
  * flags: bit0 = also compute the gradient (otherwise only out[0] and the diagnostics are valid);
  *        bits 4-7 = number of internal stream groups the latents are factored on (0 = default min(4, q_loc);
- *        1 = everything on `stream`, e.g. when the caller runs many small emulators on its own streams).
+ *        1 = everything on `stream`, e.g. when the caller runs many small emulators on its own streams);
+ *        bit8 (LCGP_FLAG_NO_LOOKAHEAD) = do not run the Cholesky panel chain on the library's internal
+ *        high-priority stream (default: it overlaps the bulk of the previous trailing update).
  * After the call the workspace holds L_k, L_k^{-T}, alpha_k (= CinvMs, lcgp.py:781) and m_k (= mks,
  * lcgp.py:779) for lcgp_predict / lcgp_get_aux -- i.e. it also replaces
  * _compute_aux_predictive_quantities_rep (lcgp.py:728-803) and compute_aux_predictive_quantities
@@ -104,6 +109,14 @@ int lcgp_predict(const lcgp_problem* prob, const double* lLmb, const double* lLm
                  void* workspace, size_t workspace_bytes, const double* x0s, int32_t n0, int32_t same_inputs,
                  void* scratch, size_t scratch_bytes, double* ghat /* q_loc x n0 */, double* gvar /* q_loc x n0 */,
                  void* stream);
+
+/* Full predictive covariance of the p outputs at each of n0 test points (predict_full with
+ * return_fullcov=True, lcgp.py:850-857):
+ *   out[i][a][b] = ystd[a] ystd[b] ( sum_k psi[k][a] gvar[k][i] psi[k][b] + [a == b] sig2[a] )
+ * psi (q x p) = phi^T * sqrt(exp(lsigma2)) as in lcgp.py:838, gvar (q x n0) from lcgp_predict, sig2 = exp(lsigma2)
+ * (p), ystd (p); out is n0 x p x p row-major.  All device pointers. */
+int lcgp_predict_fullcov(const double* psi, const double* gvar, const double* sig2, const double* ystd, int32_t q,
+                         int32_t p, int32_t n0, double* out, void* stream);
 
 /* Copies alpha (CinvMs) and m (mks), each q_loc x n, out of the workspace. */
 int lcgp_get_aux(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
@@ -141,6 +154,10 @@ int lcgp_trtri_batched(double* F, int32_t np, int32_t batch, const double* DL, c
 
 /* Library / build identification. */
 const char* lcgp_version(void);
+
+/* Number of CUDA kernels this library has launched in the calling process so far (all entry points, all
+ * threads).  bench.py reports the difference across its timed region as "gpu_launches". */
+unsigned long long lcgp_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ class Problem(C.Structure):
 
 _SIGS = {
     'lcgp_version': (C.c_char_p, []),
+    'lcgp_launch_count': (C.c_ulonglong, []),
     'lcgp_out_len': (C.c_size_t, [C.c_int32] * 3),
     'lcgp_workspace_bytes': (C.c_size_t, [C.c_int32] * 4),
     'lcgp_predict_scratch_bytes': (C.c_size_t, [C.c_int32] * 3),
@@ -37,6 +38,7 @@ _SIGS = {
                                      C.POINTER(C.c_void_p), _dp]),
     'lcgp_predict': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_size_t, _dp, C.c_int32, C.c_int32,
                                _dp, C.c_size_t, _dp, _dp, _dp]),
+    'lcgp_predict_fullcov': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     'lcgp_get_aux': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, _dp, _dp, _dp]),
     'lcgp_get_Ainv': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, C.c_int32, _dp, _dp]),
     'lcgp_kernel_matrix': (C.c_int, [_dp, C.c_int32, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, _dp]),

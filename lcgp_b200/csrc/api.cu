@@ -4,10 +4,14 @@
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
 namespace lcgp {
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- tunables (environment, read once) --------------------------------------------------------
 //   LCGP_PANEL_W  : block columns per Cholesky panel (K = 128 * W in the trailing update); default: 16 for
@@ -26,22 +30,31 @@ static int stream_groups(int q) {
     static const int v = env_int("LCGP_STREAMS", MAX_GROUPS, 1, MAX_GROUPS);
     return q < v ? q : v;
 }
+//   LCGP_LOOKAHEAD: 1 (default) = Cholesky panel chain on a high-priority stream, overlapped with the bulk of
+//                   the previous trailing update; 0 = single stream per group
+static bool lookahead_on() { static const int v = env_int("LCGP_LOOKAHEAD", 1, 0, 1); return v != 0; }
 
 // Side streams + fork/join events, created on first use for the current device.  The library
 // still allocates no device memory; these are the only objects that outlive a call.
 struct SidePool {
     int device = -1;
     cudaStream_t s[MAX_GROUPS];
-    cudaEvent_t fork, join[MAX_GROUPS];
+    cudaStream_t hp[MAX_GROUPS];                     // high-priority panel streams (Cholesky look-ahead)
+    cudaEvent_t fork, join[MAX_GROUPS], evp[MAX_GROUPS], evb[MAX_GROUPS];
     std::mutex mu;
     cudaError_t ensure() {
         int dev;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev == device) return cudaSuccess;
+        int least = 0, greatest = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return e;
         for (int i = 0; i < MAX_GROUPS; ++i) {
             if ((e = cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithPriority(&hp[i], cudaStreamNonBlocking, greatest)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&evp[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&evb[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
         if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
         device = dev;
@@ -50,21 +63,22 @@ struct SidePool {
 };
 static SidePool& side_pool() { static SidePool p; return p; }
 
-// Runs f(first_latent, count, stream) for G contiguous groups of the q latents, each on its own
-// side stream, between a fork from and a join back into `main`.
+// Runs f(first_latent, count, stream, group) for G contiguous groups of the q latents, each on its own
+// side stream, between a fork from and a join back into `main`.  The pool stays locked while work that
+// records its events is being enqueued.
 template <class F>
 static cudaError_t run_grouped(cudaStream_t main, int q, int G, F f) {
-    if (G <= 1) return f(0, q, main);
     SidePool& P = side_pool();
     std::lock_guard<std::mutex> lock(P.mu);
     cudaError_t e = P.ensure();
     if (e != cudaSuccess) return e;
+    if (G <= 1) return f(0, q, main, 0);
     if ((e = cudaEventRecord(P.fork, main)) != cudaSuccess) return e;
     int g0 = 0;
     for (int g = 0; g < G; ++g) {
         const int cnt = q / G + (g < q % G ? 1 : 0);
         if ((e = cudaStreamWaitEvent(P.s[g], P.fork, 0)) != cudaSuccess) return e;
-        if ((e = f(g0, cnt, P.s[g])) != cudaSuccess) return e;
+        if ((e = f(g0, cnt, P.s[g], g)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(P.join[g], P.s[g])) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(main, P.join[g], 0)) != cudaSuccess) return e;
         g0 += cnt;
@@ -277,22 +291,28 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     rec(0);
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * q, st));
     // b_k
-    prep_v_kernel<<<(p * q + 255) / 256, 256, 0, st>>>(p, q, lsig, P->t, P->phi, w.V);
+    note_launch(); prep_v_kernel<<<(p * q + 255) / 256, 256, 0, st>>>(p, q, lsig, P->t, P->phi, w.V);
     LCGP_CUDA(cudaGetLastError());
-    bmat_part_kernel<8><<<dim3(w.np / 128, JSPLIT, (q + 7) / 8), 128, 0, st>>>(n, w.np, p, q, w.V, P->YR, w.bpart);
+    note_launch(); bmat_part_kernel<8><<<dim3(w.np / 128, JSPLIT, (q + 7) / 8), 128, 0, st>>>(n, w.np, p, q, w.V, P->YR, w.bpart);
     LCGP_CUDA(cudaGetLastError());
-    bmat_reduce_kernel<<<(unsigned)(((size_t)q * w.np + 255) / 256), 256, 0, st>>>(w.np, q, w.bpart, w.B);
+    note_launch(); bmat_reduce_kernel<<<(unsigned)(((size_t)q * w.np + 255) / 256), 256, 0, st>>>(w.np, q, w.bpart, w.B);
     LCGP_CUDA(cudaGetLastError());
     // A_k
     LCGP_CUDA(launch_build_A(P->X, P->sr, n, d, w.np, kp, w.F, w.fstride, q, st));
     rec(1);
     int G = (flags >> 4) & 15;
     G = G == 0 ? stream_groups(q) : (G > MAX_GROUPS ? MAX_GROUPS : (G > q ? q : G));
-    auto potrf_group = [&](int g0, int cnt, cudaStream_t s) {
+    const bool look = lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD);
+    auto potrf_group = [&](int g0, int cnt, cudaStream_t s, int g) {
+        Lookahead la;
+        if (look) {   // run_grouped holds the pool lock
+            SidePool& sp = side_pool();
+            la.panel = sp.hp[g]; la.ev_panel = sp.evp[g]; la.ev_bulk = sp.evb[g];
+        }
         return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
-                             w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s);
+                             w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s, la);
     };
-    auto trtri_group = [&](int g0, int cnt, cudaStream_t s) {
+    auto trtri_group = [&](int g0, int cnt, cudaStream_t s, int) {
         return trtri_batched(sub_view(v, g0), w.T + (size_t)g0 * w.tstride, w.tstride, cnt, s);
     };
     if (ev) {
@@ -305,9 +325,9 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     } else {
         // production path: each group flows from its Cholesky straight into its triangular inverse, so
         // one group's serial panel work and launch tails overlap another group's GEMMs
-        LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s) {
-            cudaError_t e = potrf_group(g0, cnt, s);
-            return e != cudaSuccess ? e : trtri_group(g0, cnt, s);
+        LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s, int g) {
+            cudaError_t e = potrf_group(g0, cnt, s, g);
+            return e != cudaSuccess ? e : trtri_group(g0, cnt, s, g);
         }));
     }
     SolveArgs a;
@@ -319,13 +339,13 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     if (with_grad) {
         LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, g_kern + (size_t)q * d, g_kern + (size_t)q * d + q,
                                 ev ? (cudaEvent_t)ev[4] : nullptr, ev ? (cudaEvent_t)ev[5] : nullptr, st));
-        zmat_kernel<8><<<dim3((p + 7) / 8, (q + 7) / 8), 256, 0, st>>>(n, w.np, p, q, P->YR, w.mk, w.Z);
+        note_launch(); zmat_kernel<8><<<dim3((p + 7) / 8, (q + 7) / 8), 256, 0, st>>>(n, w.np, p, q, P->YR, w.mk, w.Z);
         LCGP_CUDA(cudaGetLastError());
     } else {
         rec(4);
         rec(5);
     }
-    finalize_kernel<<<1, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
+    note_launch(); finalize_kernel<<<1, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
     LCGP_CUDA(cudaGetLastError());
     rec(6);
     return 0;
@@ -336,6 +356,8 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
 using namespace lcgp;
 
 extern "C" {
+
+unsigned long long lcgp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* lcgp_version(void) { return "lcgp_b200 0.1 (sm_100a; DMMA m8n8k4 GEMM, NB=128)"; }
 
@@ -402,6 +424,12 @@ int lcgp_predict(const lcgp_problem* P, const double* lLmb, const double* lLmb0,
                                    (double*)scratch, P->q_loc, ghat, gvar, (cudaStream_t)stream));
 }
 
+int lcgp_predict_fullcov(const double* psi, const double* gvar, const double* sig2, const double* ystd, int32_t q,
+                         int32_t p, int32_t n0, double* out, void* stream) {
+    if (!psi || !gvar || !sig2 || !ystd || !out || q <= 0 || p <= 0 || n0 <= 0) return LCGP_E_ARG;
+    return cuda_rc(launch_fullcov(psi, gvar, sig2, ystd, q, p, n0, out, (cudaStream_t)stream));
+}
+
 int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
                  void* stream) {
     int rc = check_problem(P);
@@ -458,7 +486,7 @@ int lcgp_get_Ainv(const lcgp_problem* P, void* workspace, size_t workspace_bytes
     Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     const int g = (P->n + 15) / 16;
-    ainv_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(view_of(w), k, P->n, Ainv);
+    note_launch(); ainv_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(view_of(w), k, P->n, Ainv);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -487,7 +515,14 @@ int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double*
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
-    return cuda_rc(potrf_batched(v, DL, DU, batch, logdet_part, info, panel_width(), st));
+    return cuda_rc(run_grouped(st, batch, 1, [&](int, int, cudaStream_t s, int g) {
+        Lookahead la;
+        if (lookahead_on()) {
+            SidePool& sp = side_pool();
+            la.panel = sp.hp[g]; la.ev_panel = sp.evp[g]; la.ev_bulk = sp.evb[g];
+        }
+        return potrf_batched(v, DL, DU, batch, logdet_part, info, panel_width(), s, la);
+    }));
 }
 
 size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch) {

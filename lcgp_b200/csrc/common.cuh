@@ -21,6 +21,9 @@ constexpr size_t GEMM_SMEM_NMAJOR = sizeof(double) * STAGES * (A_STAGE + BN_STAG
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// Process-wide count of kernel launches made by the library (read through lcgp_launch_count()); defined in api.cu.
+void note_launch();
+
 // ---- cp.async (LDGSTS) -------------------------------------------------------------------
 // dst is a 32-bit shared-window address (computed once per kernel with __cvta_generic_to_shared, so
 // the generic->shared conversion -- an S2R of the CTA id -- stays out of the pipelined loop)

@@ -359,7 +359,7 @@ inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
+        note_launch(); gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
     } else {
         constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
         static bool configured[MAX_DEVICES] = {};
@@ -368,7 +368,7 @@ inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p, ctx.srcs);
+        note_launch(); gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p, ctx.srcs);
     }
     return cudaGetLastError();
 }
@@ -386,11 +386,13 @@ __device__ __forceinline__ void store_pair(double* C, size_t ld, const Coord& wc
 }
 
 // ---- Cholesky updates:  C[I][J] -= sum_{kb in [kb0,kb1)} P_I,kb P_J,kb^T ------------------------
-//   col <  0 : trailing update, all tiles jstart <= J <= I < nb (lower triangle of the trailing matrix)
-//   col >= 0 : left-looking update of block column `col` inside a panel: tiles (I, col), I >= col
+//   col == -1 : trailing update, all tiles jstart <= J <= I < nb (lower triangle of the trailing matrix)
+//   col == -2 : trailing update restricted to block columns jstart <= J < jend (the look-ahead part: the next
+//               panel's columns); grid.x = (jend - jstart) * (nb - jstart), tiles above the diagonal exit
+//   col >= 0  : left-looking update of block column `col` inside a panel: tiles (I, col), I >= col
 struct SyrkJob {
     static constexpr bool kBNMajor = false;
-    struct Params { FactorView v; int kb0, kb1, jstart, col; };
+    struct Params { FactorView v; int kb0, kb1, jstart, col, jend; };
     int kb0, kb1, I, J;
     double* base;
     __device__ bool init(const Params& p) {
@@ -398,6 +400,11 @@ struct SyrkJob {
             I = p.col + blockIdx.x;
             J = p.col;
             if (I >= p.v.nb) return false;
+        } else if (p.col == -2) {
+            const int R = p.v.nb - p.jstart;
+            J = p.jstart + (int)blockIdx.x / R;
+            I = p.jstart + (int)blockIdx.x % R;
+            if (J >= p.jend || I < J) return false;
         } else {
             const int T = p.v.nb - p.jstart;
             if ((int)blockIdx.x >= T * (T + 1) / 2) return false;

@@ -10,8 +10,14 @@ struct FactorView;
 struct GemmSrcs;
 
 // potrf.cu
+// Optional look-ahead resources of one Cholesky call: a (high-priority) stream for the serial panel chain and
+// two events (disable-timing) it may record freely.  panel == nullptr -> everything runs on `stream`.
+struct Lookahead {
+    cudaStream_t panel = nullptr;
+    cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
+};
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, int panel_width, cudaStream_t stream);
+                          int* info, int panel_width, cudaStream_t stream, const Lookahead& la = Lookahead());
 size_t trtri_scratch_blocks(int nb);
 void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[]);
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);
@@ -54,5 +60,9 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
 cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,
                             const double* atil, const double* x0s, int n0, int same, double* scratch,
                             int q_loc, double* ghat, double* gvar, cudaStream_t stream);
+
+// fullcov.cu
+cudaError_t launch_fullcov(const double* psi, const double* gvar, const double* sig2, const double* sv, int q, int p,
+                           int n0, double* out, cudaStream_t stream);
 
 }  // namespace lcgp

@@ -98,7 +98,7 @@ cudaError_t launch_build_A(const double* X, const double* sr, int n, int d, int 
         cudaError_t e = cudaFuncSetAttribute(build_A_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    build_A_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, smem, stream>>>(X, sr, n, d, np, kp, F, fstride);
+    note_launch(); build_A_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, smem, stream>>>(X, sr, n, d, np, kp, F, fstride);
     return cudaGetLastError();
 }
 
@@ -178,7 +178,7 @@ cudaError_t launch_matern_rect(const double* x1, int n1, const double* x2, int n
         if (e != cudaSuccess) return e;
     }
     dim3 grid((cols_out + MT - 1) / MT, (rows_out + MT - 1) / MT, batch);
-    matern_rect_kernel<<<grid, 256, smem, stream>>>(x1, n1, x2, n2, d, ell, s0, lnug, same, colscale, out,
+    note_launch(); matern_rect_kernel<<<grid, 256, smem, stream>>>(x1, n1, x2, n2, d, ell, s0, lnug, same, colscale, out,
                                                     ld_out, rows_out, cols_out, out_stride);
     return cudaGetLastError();
 }

@@ -21,6 +21,17 @@ bool gemm_use_tma() {
     return v;
 }
 
+static int env_clamped(const char* name, int dflt, int lo, int hi) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = std::atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+// LCGP_TAIL_N / LCGP_TAIL_W: panels are LCGP_TAIL_W block columns wide once at most LCGP_TAIL_N remain
+static int potrf_tail_n() { static const int v = env_clamped("LCGP_TAIL_N", 16, 0, 1 << 20); return v; }
+static int potrf_tail_w() { static const int v = env_clamped("LCGP_TAIL_W", 4, 1, 16); return v; }
+constexpr int LCGP_MAX_PANELS = 4096;
+
 int gemm_tma_min_kblocks() {
     static const int v = [] {
         const char* e = std::getenv("LCGP_TMA_MIN_KB");
@@ -256,8 +267,16 @@ static cudaError_t diag_configure() {
 // factored and the rows below solved); the matrix to the right of the panel then gets ONE trailing
 // update with K = 128 pw, which halves / quarters the C read-modify-write traffic and the number of
 // pipeline fills per flop compared with a rank-128 update per block column.
+//
+// Look-ahead (la.panel != nullptr): the serial panel chain (column update -> 58 us diagonal kernel -> panel
+// solve, ~150 us per block column) runs on the high-priority stream la.panel; the trailing update of panel k
+// is split into the NEXT panel's block columns (on la.panel, so that panel k+1 can start at once) and the
+// bulk (on `stream`), and panel k+1 is factored while the bulk of update k is still running:
+//     panel:  factor k | wait bulk k-1 | update_k(cols of panel k+1) | factor k+1 | ...
+//     bulk :            wait factor k  | update_k(cols right of panel k+1) | ...
+// Events are re-recorded every panel (a wait refers to the record that precedes it in host order).
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, int pw, cudaStream_t stream) {
+                          int* info, int pw, cudaStream_t stream, const Lookahead& la) {
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
     if (pw < 1) pw = batch >= 8 ? 16 : 8;   // auto: wide panels pay once the batch alone fills the SMs
@@ -268,30 +287,76 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
         factor_srcs(v, srcs, rows);
         if ((e = gemm_make_ctx(ctx, srcs, rows, batch)) != cudaSuccess) return e;
     }
-    for (int j0 = 0; j0 < v.nb; j0 += pw) {
-        const int j1 = (j0 + pw < v.nb) ? j0 + pw : v.nb;
+    // panel boundaries: width pw, narrowed to tail_w once at most tail_n block columns remain (there the
+    // trailing update is too small to hide the panel chain, whose column updates shorten with the panel)
+    int bounds[LCGP_MAX_PANELS + 2];
+    int npanels = 0;
+    {
+        const int tail_n = potrf_tail_n(), tail_w = potrf_tail_w();
+        int j = 0;
+        bounds[0] = 0;
+        while (j < v.nb) {
+            int w = (v.nb - j <= tail_n && tail_w < pw) ? tail_w : pw;
+            if (npanels + 1 >= LCGP_MAX_PANELS) w = v.nb - j;   // cannot happen for nb <= 8 * LCGP_MAX_PANELS
+            j = (j + w < v.nb) ? j + w : v.nb;
+            bounds[++npanels] = j;
+        }
+    }
+    const bool look = la.panel != nullptr && npanels > 1;
+    cudaStream_t ps = look ? la.panel : stream;
+    if (look) {   // the panel stream starts after everything already queued on `stream`
+        if ((e = cudaEventRecord(la.ev_bulk, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(ps, la.ev_bulk, 0)) != cudaSuccess) return e;
+    }
+    bool bulk_pending = false;   // la.ev_bulk holds a bulk update the panel stream has not yet waited for
+    for (int k = 0; k < npanels; ++k) {
+        const int j0 = bounds[k], j1 = bounds[k + 1];
         for (int j = j0; j < j1; ++j) {
             if (j > j0) {
-                SyrkJob::Params cp{v, j0, j, 0, j};
-                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), stream, j - j0);
+                SyrkJob::Params cp{v, j0, j, 0, j, 0};
+                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), ps, j - j0);
                 if (e != cudaSuccess) return e;
             }
-            potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, stream>>>(v, DLw, DUw, j, logdet_part, info);
+            note_launch(); potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, ps>>>(v, DLw, DUw, j, logdet_part, info);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             const int T = v.nb - j - 1;
             if (T > 0) {
                 TrsmJob::Params tp{v, j};
-                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), stream, 1);
+                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), ps, 1);
                 if (e != cudaSuccess) return e;
             }
         }
         const int T = v.nb - j1;
-        if (T > 0) {
-            SyrkJob::Params sp{v, j0, j1, j1, -1};
+        if (T <= 0) break;
+        if (!look) {
+            SyrkJob::Params sp{v, j0, j1, j1, -1, 0};
             e = gemm_launch<SyrkJob>(ctx, sp, dim3(T * (T + 1) / 2, batch, 1), stream, j1 - j0);
             if (e != cudaSuccess) return e;
+            continue;
         }
+        const int j2 = bounds[k + 2];                                                  // end of the next panel
+        if ((e = cudaEventRecord(la.ev_panel, ps)) != cudaSuccess) return e;            // panel k is final
+        if (bulk_pending) {                                                            // bulk k-1 wrote these columns
+            if ((e = cudaStreamWaitEvent(ps, la.ev_bulk, 0)) != cudaSuccess) return e;
+            bulk_pending = false;
+        }
+        SyrkJob::Params lp{v, j0, j1, j1, -2, j2};
+        e = gemm_launch<SyrkJob>(ctx, lp, dim3((j2 - j1) * T, batch, 1), ps, j1 - j0);
+        if (e != cudaSuccess) return e;
+        const int T2 = v.nb - j2;
+        if (T2 > 0) {
+            if ((e = cudaStreamWaitEvent(stream, la.ev_panel, 0)) != cudaSuccess) return e;
+            SyrkJob::Params sp{v, j0, j1, j2, -1, 0};
+            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T2 * (T2 + 1) / 2, batch, 1), stream, j1 - j0);
+            if (e != cudaSuccess) return e;
+            if ((e = cudaEventRecord(la.ev_bulk, stream)) != cudaSuccess) return e;
+            bulk_pending = true;
+        }
+    }
+    if (look) {   // join: `stream` continues after the last panel
+        if ((e = cudaEventRecord(la.ev_panel, ps)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, la.ev_panel, 0)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

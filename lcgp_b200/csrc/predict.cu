@@ -99,7 +99,7 @@ cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, 
     }
     e = gemm_launch<PredictJob>(ctx, p, dim3((n0p / NB) * v.nb, q_loc, 1), stream);
     if (e != cudaSuccess) return e;
-    predict_finish_kernel<<<dim3((n0 + 7) / 8, q_loc), 256, 0, stream>>>(v.np, v.nb, n0, n0p, c0s, cstride, atil, part,
+    note_launch(); predict_finish_kernel<<<dim3((n0 + 7) / 8, q_loc), 256, 0, stream>>>(v.np, v.nb, n0, n0p, c0s, cstride, atil, part,
                                                                           kp.s0, kp.D, ghat, gvar);
     return cudaGetLastError();
 }

@@ -98,18 +98,18 @@ quad_kernel(int np, const double* __restrict__ B, const double* __restrict__ mk,
 
 // gemv_part holds q_loc * nb * np partial sums followed by q_loc * np doubles for y = U^T v.
 cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream) {
-    gemv_ut_part_kernel<<<dim3(v.nb, v.nb, a.q_loc), NB, 0, stream>>>(v, a.B, a.sr, a.n, a.gemv_part);
+    note_launch(); gemv_ut_part_kernel<<<dim3(v.nb, v.nb, a.q_loc), NB, 0, stream>>>(v, a.B, a.sr, a.n, a.gemv_part);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     double* ybuf = a.gemv_part + (size_t)a.q_loc * v.nb * v.np;
-    gemv_ut_reduce_kernel<<<dim3((v.np + 255) / 256, a.q_loc), 256, 0, stream>>>(v.np, v.nb, a.gemv_part, ybuf);
+    note_launch(); gemv_ut_reduce_kernel<<<dim3((v.np + 255) / 256, a.q_loc), 256, 0, stream>>>(v.np, v.nb, a.gemv_part, ybuf);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    gemv_u_kernel<<<dim3((v.np + 7) / 8, a.q_loc), 256, 0, stream>>>(v, ybuf, a.B, a.sr, a.kp.D, a.n, a.atil,
+    note_launch(); gemv_u_kernel<<<dim3((v.np + 7) / 8, a.q_loc), 256, 0, stream>>>(v, ybuf, a.B, a.sr, a.kp.D, a.n, a.atil,
                                                                       a.alpha, a.mk);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    quad_kernel<<<a.q_loc, 256, 0, stream>>>(v.np, a.B, a.mk, a.quad);
+    note_launch(); quad_kernel<<<a.q_loc, 256, 0, stream>>>(v.np, a.B, a.mk, a.quad);
     return cudaGetLastError();
 }
 
@@ -283,7 +283,7 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
     cudaError_t e = gemm_launch<ContractJob>(ctx, p, dim3(ntiles, a.q_loc, 1), stream);
     if (ev_after) cudaEventRecord(ev_after, stream);
     if (e != cudaSuccess) return e;
-    contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
+    note_launch(); contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
     return cudaGetLastError();
 }
 

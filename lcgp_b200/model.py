@@ -107,31 +107,7 @@ class CudaEngine:
         self.d_info = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
         self.h2d_bytes = self.h_par.numel() * 8
         self.d2h_bytes = self.out_len * 8 + q * 4
-        self.launches_per_eval = self._count_launches()
         self._scratch = None
-
-    def _count_launches(self):
-        """Kernel launches of one objective+gradient evaluation (mirrors csrc/api.cu / potrf.cu)."""
-        import os
-        nb = _cabi.padded(self.n) // _cabi.NB
-        groups = min(self.q_loc, min(max(int(os.environ.get('LCGP_STREAMS', '4') or 4), 1), 4))
-        if getattr(self, 'group_flags', 0):
-            groups = min(self.q_loc, (self.group_flags >> 4) & 15)
-        pw = int(os.environ.get('LCGP_PANEL_W', '0') or 0)
-        if pw <= 0:
-            pw = 16 if (self.q_loc + groups - 1) // groups >= 8 else 8     # auto rule of csrc/potrf.cu
-        potrf = 0
-        for j0 in range(0, nb, pw):
-            j1 = min(j0 + pw, nb)
-            for j in range(j0, j1):
-                potrf += (1 if j > j0 else 0) + 1 + (1 if nb - j - 1 > 0 else 0)
-            potrf += 1 if nb - j1 > 0 else 0
-        levels, s = 0, 1
-        while s < nb:
-            levels += 1
-            s *= 2
-        # prep(3) + build(1) + groups*(potrf + trtri 2/level) + solve(4) + contract(2) + zmat + finalize
-        return 3 + 1 + groups * (potrf + 2 * levels) + 4 + 2 + 1 + 1
 
     def _stage(self, lLmb, lLmb0, lnug, lsig_p):
         q, dd = self.q_loc, self.d
@@ -807,10 +783,8 @@ class LCGP:
         yconfvar = confvar.T * self.ystd ** 2
         ypredvar = predvar.T * self.ystd ** 2
         if return_fullcov:
-            CH = torch.einsum('kn,kp->npk', torch.sqrt(gvar), psi)
-            full = CH @ CH.transpose(1, 2) + torch.diag(torch.exp(lsig_p))[None]
-            sv = self.ystd[:, 0]
-            full = full * (sv[:, None] * sv[None, :])[None]
+            # lcgp.py:850-857: n0 rank-q updates of a diagonal, written by one kernel (csrc/fullcov.cu)
+            full = _fullcov_cuda(psi, gvar, torch.exp(lsig_p), self.ystd[:, 0], self._device)
             return ypred, ypredvar, yconfvar, full
         return ypred, ypredvar, yconfvar
 
@@ -836,6 +810,29 @@ class LCGP:
         if return_fullcov:
             return ypred, ypredvar, yconfvar, None
         return ypred, ypredvar, yconfvar
+
+
+def _fullcov_cuda(psi, gvar, sig2, ystd, device=None, chunk_bytes=4 << 30):
+    """(n0, p, p) predictive covariance on the CPU, computed on the GPU in chunks of test points."""
+    _cabi.require_cuda()
+    L = _cabi.lib()
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    q, p = int(psi.shape[0]), int(psi.shape[1])
+    n0 = int(gvar.shape[1])
+    c = lambda a: a.to(dev, DT).contiguous()
+    psi_d, sig_d, sv_d = c(psi), c(sig2), c(ystd)
+    step = max(1, min(n0, int(chunk_bytes // (8 * p * p))))
+    out = torch.empty((n0, p, p), dtype=DT)
+    with torch.cuda.device(dev):
+        for s in range(0, n0, step):
+            w = min(step, n0 - s)
+            gv = c(gvar[:, s:s + w])
+            buf = torch.empty((w, p, p), dtype=DT, device=dev)
+            rc = L.lcgp_predict_fullcov(psi_d.data_ptr(), gv.data_ptr(), sig_d.data_ptr(), sv_d.data_ptr(), q, p, w,
+                                        buf.data_ptr(), _cabi.stream_ptr())
+            _cabi.check(rc, 'lcgp_predict_fullcov')
+            out[s:s + w] = buf.cpu()
+    return out
 
 
 class _LazyDiag:

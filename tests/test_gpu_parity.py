@@ -242,6 +242,26 @@ def test_fullcov_and_rep_fullcov_none():       # test_coverage_gaps.py:169-232
     assert len(out) == 4 and out[3] is None and torch.isfinite(out[0]).all()
 
 
+@pytest.mark.parametrize('q,p,n0', [(3, 3, 8), (5, 130, 37), (32, 300, 9), (70, 257, 5), (1, 1, 4), (130, 130, 3)])
+def test_fullcov_kernel_matches_formula(q, p, n0):
+    """lcgp_predict_fullcov (csrc/fullcov.cu) against lcgp.py:850-857 restated in torch on the CPU: odd / even p
+    (scalar and 16-byte stores), several 128-tiles, q below / above one 64-latent shared-memory chunk."""
+    from lcgp_b200.model import _fullcov_cuda
+    g = torch.Generator().manual_seed(q * 1000 + p)
+    psi = torch.randn(q, p, dtype=torch.float64, generator=g)
+    gvar = torch.rand(q, n0, dtype=torch.float64, generator=g) + 0.01
+    sig2 = torch.rand(p, dtype=torch.float64, generator=g) + 0.1
+    sv = torch.rand(p, dtype=torch.float64, generator=g) + 0.5
+    full = _fullcov_cuda(psi, gvar, sig2, sv)
+    CH = torch.einsum('kn,kp->npk', torch.sqrt(gvar), psi)
+    ref = (CH @ CH.transpose(1, 2) + torch.diag(sig2)[None]) * (sv[:, None] * sv[None, :])[None]
+    assert full.shape == (n0, p, p)
+    assert rel(full, ref) < 1e-13
+    assert torch.equal(full, full.transpose(1, 2))          # exactly symmetric: same products in the same order
+    small = _fullcov_cuda(psi, gvar, sig2, sv, chunk_bytes=8 * p * p * 2)      # chunked over test points
+    assert torch.equal(small, full)
+
+
 # ---------------------------------------------------------------- a10: fit
 @pytest.mark.parametrize('optimizer', ['L-BFGS-B', 'torch-lbfgs'])
 def test_fit_matches_oracle_under_shared_optimizer(optimizer):

@@ -5,7 +5,7 @@ import torch
 from lcgp_b200 import _cabi
 L = _cabi.lib(); dev = torch.device('cuda'); DT = torch.float64
 
-def run(npad, batch, reps=20):
+def run(npad, batch, reps=20, check=False):
     nb = npad // 128
     A = torch.randn(batch, npad, npad, dtype=DT, device=dev)
     A = A @ A.transpose(1, 2) / npad + 2 * torch.eye(npad, dtype=DT, device=dev)
@@ -21,6 +21,11 @@ def run(npad, batch, reps=20):
         L.lcgp_potrf_batched(F.data_ptr(), npad, batch, DLb.data_ptr(), DUb.data_ptr(), None, info.data_ptr(), st)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
+    if check:
+        Lref = torch.linalg.cholesky(A[0])
+        err = (torch.tril(F[0]) - Lref).abs().max().item() / Lref.abs().max().item()
+        print(f'   check vs torch.linalg.cholesky: max rel err {err:.2e}  info {info.tolist()}')
+        assert err < 1e-12
     ts.sort()
     flops = batch * npad ** 3 / 3
     print(f'np={npad:5d} batch={batch:3d}  median {ts[len(ts)//2]:9.1f} us  min {ts[0]:9.1f} us   {flops / (ts[len(ts)//2] * 1e-6) / 1e12:6.2f} TF/s')
@@ -28,4 +33,4 @@ def run(npad, batch, reps=20):
 import os
 CASES = [(128, 1)] if os.environ.get("DIAG_ONLY") else [(128, 1), (128, 8), (128, 32), (256, 1), (512, 1), (1024, 1), (1024, 8), (2048, 1), (2048, 10), (4096, 4), (8064, 1), (8064, 4)]
 for npad, batch in CASES:
-    run(npad, batch)
+    run(npad, batch, check=(npad in (1024, 8064) and batch == 1))
