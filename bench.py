@@ -38,7 +38,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end fit() wall-time measurement')
-    ap.add_argument('--fit-config', default='cfg3_rep')
+    ap.add_argument('--fit-config', default='cfg3_rep',
+                    help="configuration of the fit() wall-time measurement; 'workload' = the bench configuration itself "
+                         '(several minutes at config 4 on one GPU); under torchrun the fit runs only when this is given '
+                         'explicitly and is then sharded over the ranks')
     ap.add_argument('--cpu-sample-latents', type=int, default=1)
     ap.add_argument('--emulators', type=int, default=64)      # cfg5_batch only
     ap.add_argument('--threads', type=int, default=8)         # cfg5_batch only: host threads (streams) per GPU
@@ -160,13 +163,17 @@ def cpu_baseline_sample(x, y, mk, n_latents, q, threads):
     return o, fn, dt
 
 
-def fit_wall(cfg_name, with_cpu):
-    """End-to-end fit() wall time (BASELINE metric 'fit wall-s') on a configuration whose CPU cost is
-    affordable: constructor excluded, SciPy L-BFGS-B defaults, then one oracle evaluation on the host
-    cores to extrapolate the reference's fit time as evals x per-eval (labelled as such)."""
+def fit_wall(cfg_name, with_cpu, cpu_s_per_eval=None, sharded=False):
+    """End-to-end fit() wall time (BASELINE metric 'fit wall-s'): constructor excluded, SciPy L-BFGS-B
+    defaults.  The reference's fit time is extrapolated as evals x per-eval (labelled as such): per-eval from
+    one oracle evaluation on the host cores for configurations where that is affordable, else from the
+    bounded-sample CPU baseline of the same workload (`cpu_s_per_eval`).  With sharded=True every rank calls
+    this (the latents of the fitted model are sharded over the ranks, one all-reduce per evaluation)."""
     from lcgp_b200 import LCGP, synthetic
     x, y, x0, y0, mk = synthetic.make_config(cfg_name)
-    m = LCGP(y=y, x=x, **mk)
+    t0 = time.perf_counter()
+    m = LCGP(y=y, x=x, shard=sharded, **mk)
+    ctor = time.perf_counter() - t0
     m.loss_and_grad()                       # workspace allocation / first-touch outside the timed region
     m.n_evals = 0
     torch.cuda.synchronize()
@@ -174,9 +181,14 @@ def fit_wall(cfg_name, with_cpu):
     m.fit()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    out = {'config': cfg_name, 'n': int(m.n), 'q': int(m.q), 'wall_s': wall, 'evals': m.n_evals,
-           'final_loss': float(m.loss()), 'optimizer': 'L-BFGS-B (SciPy defaults)'}
-    if with_cpu:
+    out = {'config': cfg_name, 'n': int(m.n), 'q': int(m.q), 'wall_s': wall, 'evals': m.n_evals, 'ctor_s': ctor,
+           'final_loss': float(m.loss()), 'optimizer': 'L-BFGS-B (SciPy defaults)',
+           'converged': bool(getattr(m.opt_result, 'success', False)), 'iterations': int(getattr(m.opt_result, 'nit', -1))}
+    if cpu_s_per_eval is not None:
+        out['cpu_port_s_per_eval'] = cpu_s_per_eval
+        out['cpu_port_fit_s_extrapolated'] = cpu_s_per_eval * m.n_evals
+        out['cpu_note'] = 'per-eval from the bounded-sample cpu_baseline of this run'
+    elif with_cpu and int(m.n) * int(m.q) <= 40000:
         try:
             from oracle.lcgp_oracle import LCGPOracle
             torch.set_num_threads(os.cpu_count() or 1)
@@ -376,8 +388,19 @@ def run_ours(args):
         else:
             line['cpu_baseline'] = None
         line['predict'] = pred
-        if world == 1 and not args.no_fit:
-            line['fit'] = fit_wall(args.fit_config, not args.no_cpu_baseline)
+    # ---- fit wall time: every rank takes part when the fit is sharded ----
+    fit_cfg = args.config if args.fit_config == 'workload' else args.fit_config
+    fit_explicit = any(a.startswith('--fit-config') for a in sys.argv)
+    if not args.no_fit and (world == 1 or fit_explicit):
+        del model, eng
+        torch.cuda.empty_cache()
+        cpu_pe = None
+        if rank == 0 and fit_cfg == args.config and line.get('cpu_baseline') and line['cpu_baseline'].get('value'):
+            cpu_pe = 1.0 / line['cpu_baseline']['value']
+        fit = fit_wall(fit_cfg, not args.no_cpu_baseline and world == 1, cpu_pe, sharded=world > 1)
+        if rank == 0:
+            line['fit'] = fit
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

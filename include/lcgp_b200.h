@@ -78,7 +78,8 @@ size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
  * the p-vector of get_param (lcgp.py:515-532).
  * flags: bit0 = also compute the gradient (otherwise only out[0] and the diagnostics are valid);
  *        bits 4-7 = number of internal stream groups the latents are factored on (0 = default min(4, q_loc);
- *        1 = everything on `stream`, e.g. when the caller runs many small emulators on its own streams);
+ *        1 = everything on `stream` (this also disables the look-ahead below), e.g. when the caller runs many
+ *        small emulators on its own streams);
  *        bit8 (LCGP_FLAG_NO_LOOKAHEAD) = do not run the Cholesky panel chain on the library's internal
  *        high-priority stream (default: it overlaps the bulk of the previous trailing update).
  * After the call the workspace holds L_k, L_k^{-T}, alpha_k (= CinvMs, lcgp.py:781) and m_k (= mks,
@@ -117,6 +118,22 @@ int lcgp_predict(const lcgp_problem* prob, const double* lLmb, const double* lLm
  * (p), ystd (p); out is n0 x p x p row-major.  All device pointers. */
 int lcgp_predict_fullcov(const double* psi, const double* gvar, const double* sig2, const double* ystd, int32_t q,
                          int32_t p, int32_t n0, double* out, void* stream);
+
+/* ---- one-off preprocessing on the device (constructor pipeline, lcgp.py:312-324, 358-395) ----------------
+ * Replicate means: ybar[j][i] = mean of y[j][order[t]], t in [offsets[i], offsets[i+1]) -- `order` is the stable
+ * argsort of the group ids of _group_unique_rows_np (lcgp.py:349-356), offsets its n+1 segment boundaries.
+ * Replaces the Python loop of _compute_ybar_np (lcgp.py:358-367).  y: p x N, ybar: p x n. */
+int lcgp_prep_segment_mean(const double* y, const int32_t* order, const int32_t* offsets, int32_t p, int32_t N,
+                           int32_t n, double* ybar, void* stream);
+/* out[j] = k-th smallest (0-based) element of row j of Y (p x m), or of |Y[j][:] - center[j]| when center != NULL:
+ * tfp.stats.percentile(., 50, interpolation='nearest') of lcgp.py:317-318 / 388-389 with k = round((m-1)/2),
+ * exact (radix select, no interpolation). */
+int lcgp_prep_row_select(const double* Y, const double* center, int32_t p, int32_t m, int32_t k, double* out,
+                         void* stream);
+/* Ys = (Y - center_j) / spread_j (lcgp.py:320, 433); YR = Ys * r_i and w_j = sum_i r_i Ys[j][i]^2, the constant
+ * arrays lcgp_problem takes.  r == NULL means r = 1; Ys, YR, w may each be NULL when not wanted. */
+int lcgp_prep_standardize(const double* Y, const double* center, const double* spread, const double* r, int32_t p,
+                          int32_t n, double* Ys, double* YR, double* w, void* stream);
 
 /* Copies alpha (CinvMs) and m (mks), each q_loc x n, out of the workspace. */
 int lcgp_get_aux(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,

@@ -39,6 +39,9 @@ _SIGS = {
     'lcgp_predict': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_size_t, _dp, C.c_int32, C.c_int32,
                                _dp, C.c_size_t, _dp, _dp, _dp]),
     'lcgp_predict_fullcov': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
+    'lcgp_prep_segment_mean': (C.c_int, [_dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
+    'lcgp_prep_row_select': (C.c_int, [_dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
+    'lcgp_prep_standardize': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp]),
     'lcgp_get_aux': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, _dp, _dp, _dp]),
     'lcgp_get_Ainv': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, C.c_int32, _dp, _dp]),
     'lcgp_kernel_matrix': (C.c_int, [_dp, C.c_int32, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, _dp]),
@@ -81,6 +84,11 @@ def check(rc: int, what: str):
         raise LCGPError(f'{what}: CUDA error {rc - 1000}')
     names = {-1: 'invalid argument', -2: 'unsupported dimension (d > 64 or bad padding)', -3: 'workspace too small'}
     raise LCGPError(f'{what}: {names.get(rc, rc)}')
+
+
+def available() -> bool:
+    """True when the shared library has been built (says nothing about a CUDA device)."""
+    return os.path.exists(LIB_PATH)
 
 
 def require_cuda():

@@ -302,7 +302,10 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     rec(1);
     int G = (flags >> 4) & 15;
     G = G == 0 ? stream_groups(q) : (G > MAX_GROUPS ? MAX_GROUPS : (G > q ? q : G));
-    const bool look = lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD);
+    // Look-ahead uses the library's shared high-priority streams: skipped when the caller asked for "everything on
+    // my stream" (bits 4-7 == 1: many small emulators driven from several host threads would falsely serialise on
+    // them) and for small matrices, where no trailing update is big enough to hide a panel behind.
+    const bool look = lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD) && ((flags >> 4) & 15) != 1 && w.nb > 16;
     auto potrf_group = [&](int g0, int cnt, cudaStream_t s, int g) {
         Lookahead la;
         if (look) {   // run_grouped holds the pool lock
@@ -428,6 +431,24 @@ int lcgp_predict_fullcov(const double* psi, const double* gvar, const double* si
                          int32_t p, int32_t n0, double* out, void* stream) {
     if (!psi || !gvar || !sig2 || !ystd || !out || q <= 0 || p <= 0 || n0 <= 0) return LCGP_E_ARG;
     return cuda_rc(launch_fullcov(psi, gvar, sig2, ystd, q, p, n0, out, (cudaStream_t)stream));
+}
+
+int lcgp_prep_segment_mean(const double* y, const int32_t* order, const int32_t* offsets, int32_t p, int32_t N,
+                           int32_t n, double* ybar, void* stream) {
+    if (!y || !order || !offsets || !ybar || p <= 0 || N <= 0 || n <= 0 || n > N) return LCGP_E_ARG;
+    return cuda_rc(prep_segment_mean(y, order, offsets, p, N, n, ybar, (cudaStream_t)stream));
+}
+
+int lcgp_prep_row_select(const double* Y, const double* center, int32_t p, int32_t m, int32_t k, double* out,
+                         void* stream) {
+    if (!Y || !out || p <= 0 || m <= 0 || k < 0 || k >= m) return LCGP_E_ARG;
+    return cuda_rc(prep_row_select(Y, center, p, m, k, out, (cudaStream_t)stream));
+}
+
+int lcgp_prep_standardize(const double* Y, const double* center, const double* spread, const double* r, int32_t p,
+                          int32_t n, double* Ys, double* YR, double* w, void* stream) {
+    if (!Y || !center || !spread || p <= 0 || n <= 0) return LCGP_E_ARG;
+    return cuda_rc(prep_standardize(Y, center, spread, r, p, n, Ys, YR, w, (cudaStream_t)stream));
 }
 
 int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,

@@ -65,4 +65,11 @@ cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, 
 cudaError_t launch_fullcov(const double* psi, const double* gvar, const double* sig2, const double* sv, int q, int p,
                            int n0, double* out, cudaStream_t stream);
 
+// prep.cu
+cudaError_t prep_segment_mean(const double* y, const int* order, const int* off, int p, int N, int n, double* ybar,
+                              cudaStream_t st);
+cudaError_t prep_row_select(const double* Y, const double* center, int p, int m, int k, double* out, cudaStream_t st);
+cudaError_t prep_standardize(const double* Y, const double* c, const double* s, const double* r, int p, int n,
+                             double* Ys, double* YR, double* w, cudaStream_t st);
+
 }  // namespace lcgp

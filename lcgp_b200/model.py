@@ -211,7 +211,8 @@ class LCGP:
     def __init__(self, y=None, x=None, q: int = None, var_threshold: float = None,
                  diag_error_structure: list = None, parameter_clamp_flag: bool = False,
                  robust_mean: bool = True, submethod: str = 'full', rep_standardize_ybar: bool = True,
-                 verbose: bool = False, device=None, shard: bool = True, engine_factory=None, stream_groups: int = 0):
+                 verbose: bool = False, device=None, shard: bool = True, engine_factory=None, stream_groups: int = 0,
+                 device_preprocess: Optional[bool] = None):
         self.verbose = verbose
         self.robust_mean = robust_mean
         self.rep_standardize_ybar = rep_standardize_ybar
@@ -220,6 +221,19 @@ class LCGP:
         self._engine_factory = engine_factory
         self._engine = None
         self._stream_groups = stream_groups
+        # O(p N) preprocessing (replicate means, median / MAD, standardisation) on the device (csrc/prep.cu);
+        # None = wherever a CUDA device and the library are present.  The host implementation is the one
+        # SURVEY 8 a11 designates; both give the same bits except for the row sums w (reduction order).
+        if device_preprocess is None:
+            device_preprocess = engine_factory is None and torch.cuda.is_available() and _cabi.available()
+        elif device_preprocess:
+            _cabi.require_cuda()
+        self._dev_prep = bool(device_preprocess)
+        # sharding of the latents over ranks
+        self._world, self._rank = 1, 0
+        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._world = torch.distributed.get_world_size()
+            self._rank = torch.distributed.get_rank()
 
         self.x = _as_tensor2d(x)
         self.y = _as_tensor2d(y)
@@ -267,11 +281,6 @@ class LCGP:
                                  name='Latent GP nugget scale')
         self.init_params()
 
-        # sharding of the latents over ranks
-        self._world, self._rank = 1, 0
-        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
-            self._world = torch.distributed.get_world_size()
-            self._rank = torch.distributed.get_rank()
         self._local_idx = torch.arange(self.q)[self._rank::self._world]   # empty when this rank owns no latent
 
         self._invalidate_aux()
@@ -349,11 +358,44 @@ class LCGP:
             self._xnorm = self._mean_positive_distance(self.x_orig)
         return self._xnorm
 
+    def _prep_device(self):
+        return torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+
+    def _row_select_dev(self, Yd, center_d):
+        """Nearest-rank median of the rows of Yd (or of |Yd - center|) by lcgp_prep_row_select."""
+        p, m = int(Yd.shape[0]), int(Yd.shape[1])
+        k = int(np.round((m - 1) * 0.5))
+        out = torch.empty(p, dtype=DT, device=Yd.device)
+        with torch.cuda.device(Yd.device):
+            rc = _cabi.lib().lcgp_prep_row_select(Yd.data_ptr(), None if center_d is None else center_d.data_ptr(),
+                                                  p, m, k, out.data_ptr(), _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_prep_row_select')
+        return out
+
+    def _standardize_dev(self, Yd, c_d, s_d, r_d=None, want=('Ys',)):
+        """(Ys, YR, w) of lcgp_prep_standardize for the device matrix Yd; entries not in `want` are None."""
+        p, n = int(Yd.shape[0]), int(Yd.shape[1])
+        mk = lambda name, shape: torch.empty(shape, dtype=DT, device=Yd.device) if name in want else None
+        Ys, YR, w = mk('Ys', (p, n)), mk('YR', (p, n)), mk('w', (p,))
+        ptr = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(Yd.device):
+            rc = _cabi.lib().lcgp_prep_standardize(Yd.data_ptr(), c_d.data_ptr(), s_d.data_ptr(), ptr(r_d), p, n,
+                                                   ptr(Ys), ptr(YR), ptr(w), _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_prep_standardize')
+        return Ys, YR, w
+
     def _center_spread(self, Y, guard):
-        if self.robust_mean:
+        if self.robust_mean and self._dev_prep:
+            Yd = Y if Y.is_cuda else Y.to(self._prep_device(), DT).contiguous()
+            c_d = self._row_select_dev(Yd, None)
+            s_d = self._row_select_dev(Yd, c_d)
+            c, s = c_d.cpu()[:, None], s_d.cpu()[:, None]
+        elif self.robust_mean:
             c = _nearest_rank_median(Y)
             s = _nearest_rank_median(torch.abs(Y - c))
         else:
+            if Y.is_cuda:
+                Y = Y.cpu()
             c = Y.mean(dim=1, keepdim=True)
             s = Y.std(dim=1, keepdim=True, unbiased=False)
         if guard:   # lcgp.py:394 (rep path only)
@@ -362,12 +404,17 @@ class LCGP:
 
     def init_standard_y(self, y):
         """lcgp.py:312-324."""
+        if self._dev_prep:
+            yd = y.to(self._prep_device(), DT).contiguous()
+            c, s = self._center_spread(yd, guard=False)
+            ys = self._standardize_dev(yd, c[:, 0].to(yd.device), s[:, 0].to(yd.device))[0]
+            return ys.cpu(), c, s, y
         c, s = self._center_spread(y, guard=False)
         return (y - c) / s, c, s, y
 
     def _compute_center_spread_tf(self, Y):
         """lcgp.py:383-395 (name kept for drop-in use)."""
-        return self._center_spread(torch.as_tensor(Y, dtype=DT), guard=True)
+        return self._center_spread(Y if isinstance(Y, torch.Tensor) else torch.as_tensor(Y, dtype=DT), guard=True)
 
     # ------------------------------------------------------------------ replication
     def _get_raw_xy(self, x_raw=None, y_raw=None):
@@ -387,26 +434,63 @@ class LCGP:
         return xu, np.asarray(inv).reshape(-1), cnt
 
     @staticmethod
+    def _segments(inverse, n):
+        """Stable argsort of the group ids and the n+1 segment boundaries (columns of group i, in their
+        original order: order[offsets[i]:offsets[i+1]])."""
+        order = np.argsort(inverse, kind='stable')
+        offsets = np.concatenate([[0], np.cumsum(np.bincount(inverse, minlength=n))])
+        return order, offsets
+
+    @staticmethod
     def _compute_ybar_np(yr, inverse, n):
-        """Replicate means on the raw scale (lcgp.py:358-367) as one segment-sum."""
-        p = yr.shape[0]
-        sums = np.zeros((p, n), dtype=np.float64)
-        np.add.at(sums.T, inverse, yr.T)
-        return sums / np.bincount(inverse, minlength=n)[None, :]
+        """Replicate means on the raw scale (lcgp.py:358-367): the t-th replicate of every group is added in
+        one vectorised step, t = 0, 1, ..., so each group is summed left to right in its original column
+        order (what the reference's per-group numpy mean does for groups of fewer than 8 replicates)."""
+        order, offsets = LCGP._segments(inverse, n)
+        cnt = np.diff(offsets)
+        sums = np.zeros((yr.shape[0], n), dtype=np.float64)
+        for t in range(int(cnt.max())):
+            g = np.nonzero(cnt > t)[0]
+            sums[:, g] += yr[:, order[offsets[g] + t]]
+        return sums / cnt[None, :]
+
+    def _compute_ybar_dev(self, yr, inverse, n):
+        """Same on the device (lcgp_prep_segment_mean); returns the device tensor."""
+        order, offsets = self._segments(inverse, n)
+        dev = self._prep_device()
+        yd = torch.as_tensor(yr, dtype=DT).to(dev).contiguous()
+        od = torch.as_tensor(order.astype(np.int32)).to(dev)
+        fd = torch.as_tensor(offsets.astype(np.int32)).to(dev)
+        p, N = int(yd.shape[0]), int(yd.shape[1])
+        ybar = torch.empty((p, n), dtype=DT, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().lcgp_prep_segment_mean(yd.data_ptr(), od.data_ptr(), fd.data_ptr(), p, N, n, ybar.data_ptr(),
+                                                    _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_prep_segment_mean')
+        return ybar
 
     def preprocess(self, y_raw=None, x_raw=None):
         """lcgp.py:397-426: 12-tuple of replication structures."""
         xr, yr, N, d, p = self._get_raw_xy(x_raw=x_raw, y_raw=y_raw)
         xu, inv, cnt = self._group_unique_rows_np(xr)
         n_unique = int(xu.shape[0])
-        ybar = torch.as_tensor(self._compute_ybar_np(yr, inv, n_unique), dtype=DT)
+        ybar_d = None
+        if self._dev_prep:
+            ybar_d = self._compute_ybar_dev(yr, inv, n_unique)
+            ybar = ybar_d.cpu()
+        else:
+            ybar = torch.as_tensor(self._compute_ybar_np(yr, inv, n_unique), dtype=DT)
         x_unique = torch.as_tensor(xu, dtype=DT)
         x_unique_s = (x_unique - self.x_min) / (self.x_max - self.x_min)
         group_ids = torch.as_tensor(inv, dtype=torch.int32)
         r = torch.as_tensor(cnt.astype(np.int32))
         R = _LazyDiag(r)
-        ybar_mean, ybar_std = self._compute_center_spread_tf(ybar)
-        ybar_s = (ybar - ybar_mean) / ybar_std
+        if ybar_d is not None:
+            ybar_mean, ybar_std = self._compute_center_spread_tf(ybar_d)
+            ybar_s = self._standardize_dev(ybar_d, ybar_mean[:, 0].to(ybar_d.device), ybar_std[:, 0].to(ybar_d.device))[0].cpu()
+        else:
+            ybar_mean, ybar_std = self._compute_center_spread_tf(ybar)
+            ybar_s = (ybar - ybar_mean) / ybar_std
         return (x_unique, x_unique_s, group_ids, r, R, ybar, ybar_s, ybar_mean, ybar_std,
                 _itensor(n_unique), _itensor(d), _itensor(p))
 
@@ -434,7 +518,7 @@ class LCGP:
         """lcgp.py:454-485: phi = U_q sqrt(n) / s_q from the SVD of the (standardised) outputs."""
         Y = self._get_phi_input()
         n, p = int(self.n), int(self.p)
-        U, s, _ = torch.linalg.svd(Y, full_matrices=False)
+        U, s = self._svd_basis(Y)
         if (self.q is None) and (var_threshold is None):
             q = p
         elif (self.q is None) and (var_threshold is not None):
@@ -450,6 +534,32 @@ class LCGP:
             print('======= VARIANCE OF G ======')
             print(g.var(dim=1, unbiased=False))
         return g, phi, diag_D, q
+
+    def _svd_basis(self, Y):
+        """Left singular vectors and singular values of Y (p x n) by LAPACK on the host.  With the latents
+        sharded over ranks, rank 0 alone factors (with the host threads the other ranks would otherwise
+        fight over) and broadcasts U, s: N concurrent SVDs on one host were the dominant construction
+        cost, and every rank then holds bit-identical phi."""
+        if self._world == 1:
+            U, s, _ = torch.linalg.svd(Y, full_matrices=False)
+            return U, s
+        import os
+        dist = torch.distributed
+        dev = self._collective_device()
+        r = min(Y.shape)
+        if self._rank == 0:
+            prev = torch.get_num_threads()
+            torch.set_num_threads(max(prev, (os.cpu_count() or 1) - self._world + 1))
+            try:
+                U, s, _ = torch.linalg.svd(Y, full_matrices=False)
+            finally:
+                torch.set_num_threads(prev)
+            buf = torch.cat([U.reshape(-1), s]).to(dev)
+        else:
+            buf = torch.empty(Y.shape[0] * r + r, dtype=DT, device=dev)
+        dist.broadcast(buf, src=0)
+        buf = buf.cpu()
+        return buf[:Y.shape[0] * r].reshape(Y.shape[0], r), buf[Y.shape[0] * r:]
 
     # ------------------------------------------------------------------ parameters
     def init_params(self):
@@ -502,9 +612,16 @@ class LCGP:
             Ybar = self.y
             t = torch.ones(int(self.p), dtype=DT)
             scale = 1.0
-        YR = Ybar * r[None, :]
+        if self._dev_prep:    # YR and w by lcgp_prep_standardize with centre 0 / spread 1 (exact), on the device
+            dev = self._prep_device()
+            p = int(self.p)
+            zero, one = torch.zeros(p, dtype=DT, device=dev), torch.ones(p, dtype=DT, device=dev)
+            _, YR, w = self._standardize_dev(Ybar.to(dev, DT).contiguous(), zero, one, r.to(dev), want=('YR', 'w'))
+        else:
+            YR = Ybar * r[None, :]
+            w = (YR * Ybar).sum(dim=1)
         return dict(n=int(self.n), d=int(self.d), p=int(self.p), X=X, sr=torch.sqrt(r), YR=YR,
-                    w=(YR * Ybar).sum(dim=1), t=t, scale=scale, sum_log_r=float(torch.log(r).sum()))
+                    w=w, t=t, scale=scale, sum_log_r=float(torch.log(r).sum()))
 
     @property
     def engine(self):

@@ -262,6 +262,51 @@ def test_fullcov_kernel_matches_formula(q, p, n0):
     assert torch.equal(small, full)
 
 
+# ---------------------------------------------------------------- f-1: preprocessing on the device
+@pytest.mark.parametrize('sub,robust', [('rep', True), ('rep', False), ('full', True), ('full', False)])
+def test_device_preprocessing_equals_host_preprocessing(sub, robust):
+    """csrc/prep.cu (replicate means, nearest-rank median / MAD, standardisation) vs the host pipeline of
+    lcgp.py:312-324, 358-395: identical bits for every attribute; the objective's row sums w to 1e-14."""
+    if sub == 'rep':
+        x, y, _ = make_ragged_rep_data(seed=21, n_unique=333, p=7, d=3)
+    else:
+        x, y = make_full_data(seed=22, n=301, p=6, d=2)
+    md = LCGP(y=y, x=x, q=3, submethod=sub, robust_mean=robust, device_preprocess=True)
+    mh = LCGP(y=y, x=x, q=3, submethod=sub, robust_mean=robust, device_preprocess=False)
+    names = ('ybar', 'ybar_mean', 'ybar_std', 'ybar_s') if sub == 'rep' else ('y', 'ymean', 'ystd')
+    for nm in names:
+        assert torch.equal(getattr(md, nm), getattr(mh, nm)), nm
+    assert torch.equal(md.phi, mh.phi) and torch.equal(md.diag_D, mh.diag_D)
+    dd, dh = md._problem_data(), mh._problem_data()
+    assert dd['YR'].is_cuda and torch.equal(dd['YR'].cpu(), dh['YR'])
+    assert rel(dd['w'].cpu(), dh['w']) < 1e-14
+    fd, gd = md.loss_and_grad()
+    fh, gh = mh.loss_and_grad()
+    assert abs(fd - fh) <= 1e-13 * abs(fh) and np.max(np.abs(gd - gh)) <= 1e-12 * np.max(np.abs(gh))
+
+
+@pytest.mark.parametrize('m', [1, 2, 7, 256, 1001, 8000])
+def test_row_select_is_the_nearest_rank_percentile(m):
+    """lcgp_prep_row_select == sorted row at index round((m-1)/2) (tfp 'nearest' percentile), incl. ties, negative
+    values, zeros and the |y - c| form."""
+    from lcgp_b200 import _cabi
+    g = torch.Generator().manual_seed(m)
+    Y = torch.randn(5, m, dtype=torch.float64, generator=g)
+    Y[1] = torch.round(Y[1] * 2) / 2                 # many ties, exact zeros
+    Y[2] = -torch.abs(Y[2])                          # all negative
+    Y[3] = Y[3] * 1e-300                             # tiny magnitudes
+    Y[4] = 3.25
+    k = int(np.round((m - 1) * 0.5))
+    Yd = Y.cuda()
+    out = torch.empty(5, dtype=torch.float64, device='cuda')
+    _cabi.check(_cabi.lib().lcgp_prep_row_select(Yd.data_ptr(), None, 5, m, k, out.data_ptr(), _cabi.stream_ptr()), 'select')
+    want = torch.sort(Y, dim=1).values[:, k]
+    assert torch.equal(out.cpu(), want)
+    c = want.cuda()
+    _cabi.check(_cabi.lib().lcgp_prep_row_select(Yd.data_ptr(), c.data_ptr(), 5, m, k, out.data_ptr(), _cabi.stream_ptr()), 'select')
+    assert torch.equal(out.cpu(), torch.sort(torch.abs(Y - want[:, None]), dim=1).values[:, k])
+
+
 # ---------------------------------------------------------------- a10: fit
 @pytest.mark.parametrize('optimizer', ['L-BFGS-B', 'torch-lbfgs'])
 def test_fit_matches_oracle_under_shared_optimizer(optimizer):

@@ -131,6 +131,31 @@ def test_preprocessing_matches_oracle(sub, robust, std):
         assert float((a - b.detach()).abs().max()) < 1e-12
 
 
+def test_replicate_means_follow_the_reference_loop():
+    """_compute_ybar_np (segmented sum over group-sorted columns) == the reference's per-group loop
+    `ybar[:, i] = y[:, inverse == i].mean(axis=1)` (lcgp.py:358-367) on ragged replication, to summation-order
+    rounding (numpy's mean adds groups of >= 8 replicates with 8 interleaved partial sums, the segmented sum
+    left to right); identical bits for groups of fewer than 8."""
+    x, y, xu = make_ragged_rep_data(seed=4, n_unique=57, p=6, d=2)
+    xr, inv, cnt = LCGP._group_unique_rows_np(np.asarray(x))
+    n = xr.shape[0]
+    yr = np.asarray(y)
+    loop = np.stack([yr[:, inv == i].mean(axis=1) for i in range(n)], axis=1)
+    got = LCGP._compute_ybar_np(yr, inv, n)
+    assert got.shape == (6, n) and np.allclose(got, loop, rtol=4e-16 * cnt.max(), atol=1e-300)
+    heavy = make_ragged_rep_data(seed=5, n_unique=9, p=3, d=1)
+    xh, ih, ch = LCGP._group_unique_rows_np(np.asarray(np.repeat(heavy[0], 5, axis=0)))      # groups of >= 8 too
+    yh = np.random.default_rng(0).normal(size=(3, ih.size))
+    lh = np.stack([yh[:, ih == i].mean(axis=1) for i in range(xh.shape[0])], axis=1)
+    assert ch.max() >= 8 and np.allclose(LCGP._compute_ybar_np(yh, ih, xh.shape[0]), lh, rtol=4e-16 * ch.max(), atol=1e-300)
+    small = cnt < 8
+    assert small.any() and np.array_equal(got[:, small], loop[:, small])
+    order, off = LCGP._segments(inv, n)
+    assert off[0] == 0 and off[-1] == yr.shape[1] and np.array_equal(np.diff(off), cnt)
+    for i in (0, n // 2, n - 1):          # stable: original column order inside each group
+        assert np.array_equal(order[off[i]:off[i + 1]], np.nonzero(inv == i)[0])
+
+
 def test_xnorm_sort_formula_matches_dense_definition():
     rng = np.random.default_rng(0)
     x = torch.as_tensor(np.round(rng.uniform(0, 1, (70, 2)), 1))    # many ties

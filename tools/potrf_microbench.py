@@ -31,6 +31,6 @@ def run(npad, batch, reps=20, check=False):
     print(f'np={npad:5d} batch={batch:3d}  median {ts[len(ts)//2]:9.1f} us  min {ts[0]:9.1f} us   {flops / (ts[len(ts)//2] * 1e-6) / 1e12:6.2f} TF/s')
 
 import os
-CASES = [(128, 1)] if os.environ.get("DIAG_ONLY") else [(128, 1), (128, 8), (128, 32), (256, 1), (512, 1), (1024, 1), (1024, 8), (2048, 1), (2048, 10), (4096, 4), (8064, 1), (8064, 4)]
+CASES = [(128, 1)] if os.environ.get("DIAG_ONLY") else [tuple(int(v) for v in c.split('x')) for c in os.environ["CASES"].split(',')] if os.environ.get("CASES") else [(128, 1), (128, 8), (128, 32), (256, 1), (512, 1), (1024, 1), (1024, 8), (2048, 1), (2048, 10), (4096, 4), (8064, 1), (8064, 4)]
 for npad, batch in CASES:
     run(npad, batch, check=(npad in (1024, 8064) and batch == 1))
