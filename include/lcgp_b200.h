@@ -7,7 +7,8 @@
  * Conventions
  *   - every array argument is a DEVICE pointer to row-major contiguous IEEE fp64 unless its name
  *     ends in _host; the caller (torch) owns every buffer including the workspace; the library
- *     allocates nothing and keeps no state between calls
+ *     allocates no device memory and keeps no state between calls (exceptions: a process-wide pool of
+ *     side streams / events, and the explicit lcgp_plan objects)
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns
  *     without synchronising (the *_host variants synchronise the stream before returning)
  *   - return value: 0 = ok; < 0 = invalid argument (LCGP_E_*); >= 1000 = 1000 + cudaError_t.
@@ -101,6 +102,23 @@ int lcgp_nll_grad_host(const lcgp_problem* prob, const double* lLmb_host, const 
                        const double* lnugGPs_host, const double* lsigma2_p_host, void* workspace,
                        size_t workspace_bytes, double* out_host, int32_t* info_host, int32_t flags,
                        void* const* stage_events, void* stream);
+
+/* Evaluation plan: lcgp_nll_grad_host with fixed buffers, captured once as a CUDA graph (parameter upload, every
+ * kernel, result download) and replayed with one launch per evaluation.  Evaluations of small problems are bound
+ * by the kernel-launch rate -- above all when several host threads fit independent emulators on one GPU (BASELINE
+ * config 5) -- not by the GPU.  params_host = [lLmb (q_loc x d) | lLmb0 (q_loc) | lnugGPs (q_loc) | lsigma2_p (p)],
+ * out_host (lcgp_out_len doubles) and info_host (q_loc) must stay valid (pinned host memory) for the life of the
+ * plan; the caller rewrites params_host before each lcgp_plan_run.  lcgp_plan_run synchronises `stream`.  The plan
+ * is the one object the library allocates for the caller (host memory + the graph); lcgp_plan_destroy frees it.
+ * A plan always runs on `stream` alone (the stream-group bits of `flags` are forced to 1), and `stream` must not
+ * be the legacy default stream, which cannot be captured.  If the driver refuses the capture the plan runs the
+ * same kernels launch by launch (lcgp_plan_is_graph tells which). */
+typedef struct lcgp_plan lcgp_plan;
+int lcgp_plan_create(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, const double* params_host,
+                     double* out_host, int32_t* info_host, int32_t flags, lcgp_plan** plan);
+int lcgp_plan_run(lcgp_plan* plan, void* stream);
+int lcgp_plan_is_graph(const lcgp_plan* plan);
+void lcgp_plan_destroy(lcgp_plan* plan);
 
 /* Latent predictive mean and variance at n0 standardised test inputs, from the factor left in the
  * workspace by the last lcgp_nll_grad with the same parameters.

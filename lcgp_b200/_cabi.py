@@ -36,6 +36,10 @@ _SIGS = {
                                 C.POINTER(C.c_void_p), _dp]),
     'lcgp_nll_grad_host': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp, _dp, C.c_int32,
                                      C.POINTER(C.c_void_p), _dp]),
+    'lcgp_plan_create': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, _dp, _dp, _dp, C.c_int32, C.POINTER(C.c_void_p)]),
+    'lcgp_plan_run': (C.c_int, [C.c_void_p, _dp]),
+    'lcgp_plan_is_graph': (C.c_int, [C.c_void_p]),
+    'lcgp_plan_destroy': (None, [C.c_void_p]),
     'lcgp_predict': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_size_t, _dp, C.c_int32, C.c_int32,
                                _dp, C.c_size_t, _dp, _dp, _dp]),
     'lcgp_predict_fullcov': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),

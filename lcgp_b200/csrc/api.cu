@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <new>
 
 namespace lcgp {
 
@@ -67,7 +68,8 @@ static SidePool& side_pool() { static SidePool p; return p; }
 // side stream, between a fork from and a join back into `main`.  The pool stays locked while work that
 // records its events is being enqueued.
 template <class F>
-static cudaError_t run_grouped(cudaStream_t main, int q, int G, F f) {
+static cudaError_t run_grouped(cudaStream_t main, int q, int G, bool need_pool, F f) {
+    if (G <= 1 && !need_pool) return f(0, q, main, 0);   // nothing shared is touched: concurrent callers do not serialise
     SidePool& P = side_pool();
     std::lock_guard<std::mutex> lock(P.mu);
     cudaError_t e = P.ensure();
@@ -321,14 +323,14 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     if (ev) {
         // stage timing requested: join the groups between Cholesky and triangular inverse so that the
         // two stages can be timed separately
-        LCGP_CUDA(run_grouped(st, q, G, potrf_group));
+        LCGP_CUDA(run_grouped(st, q, G, look, potrf_group));
         rec(2);
-        LCGP_CUDA(run_grouped(st, q, G, trtri_group));
+        LCGP_CUDA(run_grouped(st, q, G, false, trtri_group));
         rec(3);
     } else {
         // production path: each group flows from its Cholesky straight into its triangular inverse, so
         // one group's serial panel work and launch tails overlap another group's GEMMs
-        LCGP_CUDA(run_grouped(st, q, G, [&](int g0, int cnt, cudaStream_t s, int g) {
+        LCGP_CUDA(run_grouped(st, q, G, look, [&](int g0, int cnt, cudaStream_t s, int g) {
             cudaError_t e = potrf_group(g0, cnt, s, g);
             return e != cudaSuccess ? e : trtri_group(g0, cnt, s, g);
         }));
@@ -411,6 +413,107 @@ int lcgp_nll_grad_host(const lcgp_problem* P, const double* lLmb_h, const double
     LCGP_CUDA(cudaMemcpyAsync(info_h, w.info, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
     LCGP_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+}  // extern "C"
+
+// ---- evaluation plans: one objective(+gradient) evaluation captured as a CUDA graph -----------------------
+// Small problems (n <= 2048: ~100 kernels of 20-60 us) are bound by the driver's launch rate, not by the GPU --
+// above all when several host threads fit independent emulators on one device (BASELINE config 5) and serialise
+// on the context lock.  A plan captures the parameter upload, every kernel of lcgp_nll_grad (including the fork /
+// join over the internal stream groups) and the result download ONCE and replays it with a single launch.
+struct lcgp_plan {
+    lcgp_problem prob;
+    void* ws;
+    size_t ws_bytes;
+    const double* par_h;   // [lLmb | lLmb0 | lnugGPs | lsigma2_p], pinned host memory owned by the caller
+    double* out_h;
+    int32_t* info_h;
+    int32_t flags;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool eager = false;    // capture was refused once: run the plain call from now on
+};
+
+static int plan_enqueue(const lcgp_plan* pl, cudaStream_t st) {
+    const lcgp_problem* P = &pl->prob;
+    const int q = P->q_loc, d = P->d, p = P->p;
+    Workspace w = layout(P->n, d, p, q, pl->ws);
+    const double* h = pl->par_h;
+    LCGP_CUDA(cudaMemcpyAsync(w.ell, h, sizeof(double) * q * d, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.s0, h + (size_t)q * d, sizeof(double) * q, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lnug, h + (size_t)q * d + q, sizeof(double) * q, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lsig, h + (size_t)q * d + 2 * q, sizeof(double) * p, cudaMemcpyHostToDevice, st));
+    int rc = nll_grad_impl(P, w.ell, w.s0, w.lnug, w.lsig, w, w.out, w.info, pl->flags, nullptr, st);
+    if (rc) return rc;
+    LCGP_CUDA(cudaMemcpyAsync(pl->out_h, w.out, sizeof(double) * lcgp_out_len(p, d, q), cudaMemcpyDeviceToHost, st));
+    LCGP_CUDA(cudaMemcpyAsync(pl->info_h, w.info, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+extern "C" {
+
+int lcgp_plan_create(const lcgp_problem* P, void* workspace, size_t workspace_bytes, const double* params_host,
+                     double* out_host, int32_t* info_host, int32_t flags, lcgp_plan** plan) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!workspace || !params_host || !out_host || !info_host || !plan) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    lcgp_plan* pl = new (std::nothrow) lcgp_plan();
+    if (!pl) return LCGP_E_ARG;
+    pl->prob = *P; pl->ws = workspace; pl->ws_bytes = workspace_bytes;
+    pl->par_h = params_host; pl->out_h = out_host; pl->info_h = info_host;
+    // a plan always runs on the caller's stream alone (stream-group bits forced to 1, which also switches the
+    // look-ahead off): the library's shared side streams must not be pulled into one thread's capture
+    pl->flags = (flags & ~0xF0) | (1 << 4);
+    *plan = pl;
+    return 0;
+}
+
+int lcgp_plan_run(lcgp_plan* pl, void* stream) {
+    if (!pl) return LCGP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!pl->exec && !pl->eager) {
+        // warm the lazily-set kernel attributes and the stream pool outside the capture
+        int rc = plan_enqueue(pl, st);
+        if (rc) return rc;
+        LCGP_CUDA(cudaStreamSynchronize(st));
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = plan_enqueue(pl, st);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ec = cudaStreamEndCapture(st, &g);
+            if (rc == 0 && ec == cudaSuccess && g && cudaGraphInstantiate(&pl->exec, g, 0) == cudaSuccess) {
+                pl->graph = g;
+            } else {
+                if (g) cudaGraphDestroy(g);
+                pl->exec = nullptr;
+                pl->eager = true;
+                (void)cudaGetLastError();   // clear the capture error; the eager path below still runs on the GPU
+            }
+        } else {
+            pl->eager = true;
+            (void)cudaGetLastError();
+        }
+    }
+    if (pl->exec) {
+        note_launch();   // the graph launch itself; its kernel nodes were counted when they were captured
+        LCGP_CUDA(cudaGraphLaunch(pl->exec, st));
+    } else {
+        int rc = plan_enqueue(pl, st);
+        if (rc) return rc;
+    }
+    LCGP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int lcgp_plan_is_graph(const lcgp_plan* pl) { return pl && pl->exec ? 1 : 0; }
+
+void lcgp_plan_destroy(lcgp_plan* pl) {
+    if (!pl) return;
+    if (pl->exec) cudaGraphExecDestroy(pl->exec);
+    if (pl->graph) cudaGraphDestroy(pl->graph);
+    delete pl;
 }
 
 int lcgp_predict(const lcgp_problem* P, const double* lLmb, const double* lLmb0, const double* lnugGPs,
@@ -536,7 +639,7 @@ int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double*
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
-    return cuda_rc(run_grouped(st, batch, 1, [&](int, int, cudaStream_t s, int g) {
+    return cuda_rc(run_grouped(st, batch, 1, lookahead_on(), [&](int, int, cudaStream_t s, int g) {
         Lookahead la;
         if (lookahead_on()) {
             SidePool& sp = side_pool();

@@ -28,7 +28,7 @@ static int env_clamped(const char* name, int dflt, int lo, int hi) {
     return v < lo ? lo : (v > hi ? hi : v);
 }
 // LCGP_TAIL_N / LCGP_TAIL_W: panels are LCGP_TAIL_W block columns wide once at most LCGP_TAIL_N remain
-static int potrf_tail_n() { static const int v = env_clamped("LCGP_TAIL_N", 16, 0, 1 << 20); return v; }
+static int potrf_tail_n() { static const int v = env_clamped("LCGP_TAIL_N", 24, 0, 1 << 20); return v; }
 static int potrf_tail_w() { static const int v = env_clamped("LCGP_TAIL_W", 4, 1, 16); return v; }
 constexpr int LCGP_MAX_PANELS = 4096;
 

@@ -16,6 +16,7 @@ replicated host optimizer stays in lock-step.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -107,6 +108,11 @@ class CudaEngine:
         self.d_info = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
         self.h2d_bytes = self.h_par.numel() * 8
         self.d2h_bytes = self.out_len * 8 + q * 4
+        # launch-bound sizes (n <= 2048): evaluations replay a captured CUDA graph (lcgp_plan_*), on a stream of
+        # the engine's own because the legacy default stream cannot be captured
+        self.use_plans = _cabi.padded(self.n) // _cabi.NB <= 16 and os.environ.get('LCGP_GRAPHS', '1') != '0'
+        self._plans = {}
+        self._plan_stream = torch.cuda.Stream(device=dev) if self.use_plans else None
         self._scratch = None
 
     def _stage(self, lLmb, lLmb0, lnug, lsig_p):
@@ -130,6 +136,10 @@ class CudaEngine:
         lcgp_nll_grad_host call (H2D of the parameters, all kernels, D2H of the result, sync)."""
         o1, o2, o3 = self._stage(lLmb, lLmb0, lnug, lsig_p)
         base = self.h_par.data_ptr()
+        if self.use_plans and events is None:
+            self._run_plan(int(bool(with_grad)) | self.group_flags)
+            self._check_info(self.h_info)
+            return self.h_out.clone()
         with torch.cuda.device(self.device):
             rc = self.lib.lcgp_nll_grad_host(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
                                              self.ws.data_ptr(), self.ws_bytes, self.h_out.data_ptr(),
@@ -138,6 +148,31 @@ class CudaEngine:
         _cabi.check(rc, 'lcgp_nll_grad_host')
         self._check_info(self.h_info)
         return self.h_out.clone()
+
+    def _run_plan(self, flags):
+        import ctypes as C
+        plan = self._plans.get(flags)
+        with torch.cuda.device(self.device):
+            if plan is None:
+                h = C.c_void_p()
+                rc = self.lib.lcgp_plan_create(self.prob, self.ws.data_ptr(), self.ws_bytes, self.h_par.data_ptr(),
+                                               self.h_out.data_ptr(), self.h_info.data_ptr(), flags, C.byref(h))
+                _cabi.check(rc, 'lcgp_plan_create')
+                plan = self._plans[flags] = h
+            self._plan_stream.wait_stream(torch.cuda.current_stream())     # constants / earlier work on the caller's stream
+            rc = self.lib.lcgp_plan_run(plan, self._plan_stream.cuda_stream)  # synchronises the plan stream
+        _cabi.check(rc, 'lcgp_plan_run')
+
+    def plan_is_graph(self):
+        """True when every plan created so far replays a captured graph (False: none yet, or capture refused)."""
+        return bool(self._plans) and all(self.lib.lcgp_plan_is_graph(h) for h in self._plans.values())
+
+    def __del__(self):
+        try:
+            for h in getattr(self, '_plans', {}).values():
+                self.lib.lcgp_plan_destroy(h)
+        except Exception:
+            pass
 
     def evaluate_device(self, lLmb, lLmb0, lnug, lsig_p, with_grad=True, events=None):
         """Same, but the result stays on the device (multi-rank path: all-reduce follows on the

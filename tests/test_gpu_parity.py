@@ -262,6 +262,48 @@ def test_fullcov_kernel_matches_formula(q, p, n0):
     assert torch.equal(small, full)
 
 
+# ---------------------------------------------------------------- evaluation plans (CUDA graphs)
+def test_plan_replays_a_graph_and_equals_the_launch_by_launch_path():
+    """Small problems evaluate through lcgp_plan_run: the capture must succeed (a real graph, not the eager
+    fallback) and replaying it at new parameter values must give the bits of the launch-by-launch call."""
+    x, y, _ = make_ragged_rep_data(seed=31, n_unique=150, p=5, d=3)
+    mg = LCGP(y=y, x=x, q=4, submethod='rep')
+    me = LCGP(y=y, x=x, q=4, submethod='rep')
+    assert mg.engine.use_plans
+    me.engine.use_plans = False
+    from lcgp_b200 import _cabi
+    for step in range(4):
+        if step:
+            move_params(mg, seed=100 + step); move_params(me, seed=100 + step)
+        c0 = int(_cabi.lib().lcgp_launch_count())
+        fg, gg = mg.loss_and_grad()
+        c1 = int(_cabi.lib().lcgp_launch_count())
+        fe, ge = me.loss_and_grad()
+        c2 = int(_cabi.lib().lcgp_launch_count())
+        assert fg == fe and np.array_equal(gg, ge)
+        if step:                                   # replay = one graph launch; the eager path launches every kernel
+            assert c1 - c0 == 1 and c2 - c1 > 20
+    assert mg.engine.plan_is_graph()
+    assert float(mg.loss()) == float(me.loss())    # the objective-only plan (flags without the gradient bit)
+    x0 = np.random.default_rng(3).uniform(0, 1, (9, 3))
+    for a, b in zip(mg.predict(x0), me.predict(x0)):   # prediction reads the factor the replay left in the workspace
+        assert torch.equal(a, b)
+
+
+def test_batched_emulators_on_threads_match_sequential_fits():
+    """fit_emulators (BASELINE config 5 path: several host threads, one stream and one graph plan each) gives
+    exactly the parameters of one-at-a-time fits."""
+    from lcgp_b200 import fit_emulators
+    data = [make_full_data(seed=40 + i, n=140, p=4, d=2) for i in range(5)]
+    mk = dict(q=2, submethod='full')
+    res = fit_emulators(data, mk, fit_options=dict(maxiter=6), threads_per_gpu=3)
+    for (x, y), r in zip(data, res):
+        m = LCGP(y=y, x=x, **mk)
+        m.fit(maxiter=6)
+        assert np.array_equal(m.get_param()[0].numpy(), r['lLmb']) and m.n_evals + 0 >= 1
+        assert abs(float(m.loss()) - r['loss']) == 0.0
+
+
 # ---------------------------------------------------------------- f-1: preprocessing on the device
 @pytest.mark.parametrize('sub,robust', [('rep', True), ('rep', False), ('full', True), ('full', False)])
 def test_device_preprocessing_equals_host_preprocessing(sub, robust):
