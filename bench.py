@@ -44,7 +44,7 @@ def parse():
                          'explicitly and is then sharded over the ranks')
     ap.add_argument('--cpu-sample-latents', type=int, default=1)
     ap.add_argument('--emulators', type=int, default=64)      # cfg5_batch only
-    ap.add_argument('--threads', type=int, default=8)         # cfg5_batch only: host threads (streams) per GPU
+    ap.add_argument('--threads', type=int, default=4)         # cfg5_batch only: host threads (streams) per GPU (more only contend for the GIL)
     ap.add_argument('--maxiter', type=int, default=30)        # cfg5_batch only: L-BFGS-B iteration budget per emulator
     return ap.parse_args()
 

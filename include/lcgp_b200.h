@@ -110,9 +110,11 @@ int lcgp_nll_grad_host(const lcgp_problem* prob, const double* lLmb_host, const 
  * out_host (lcgp_out_len doubles) and info_host (q_loc) must stay valid (pinned host memory) for the life of the
  * plan; the caller rewrites params_host before each lcgp_plan_run.  lcgp_plan_run synchronises `stream`.  The plan
  * is the one object the library allocates for the caller (host memory + the graph); lcgp_plan_destroy frees it.
- * A plan always runs on `stream` alone (the stream-group bits of `flags` are forced to 1), and `stream` must not
- * be the legacy default stream, which cannot be captured.  If the driver refuses the capture the plan runs the
- * same kernels launch by launch (lcgp_plan_is_graph tells which). */
+ * A plan runs on ONE private stream of its own (the stream-group bits of `flags` are forced to 1; a private
+ * stream because a stream under capture must not be touched by another thread, and frameworks hand out pooled
+ * streams), ordered after everything already queued on `stream`; the first lcgp_plan_run evaluates launch by
+ * launch and then captures.  If the driver refuses the capture the plan keeps running the same kernels launch by
+ * launch (lcgp_plan_is_graph tells which). */
 typedef struct lcgp_plan lcgp_plan;
 int lcgp_plan_create(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, const double* params_host,
                      double* out_host, int32_t* info_host, int32_t flags, lcgp_plan** plan);

@@ -433,6 +433,8 @@ struct lcgp_plan {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool eager = false;    // capture was refused once: run the plain call from now on
+    cudaStream_t own = nullptr;   // the plan's private stream: captured / replayed on, never shared with another plan
+    cudaEvent_t ev = nullptr;     // orders the plan stream after the caller's stream
 };
 
 static int plan_enqueue(const lcgp_plan* pl, cudaStream_t st) {
@@ -473,9 +475,17 @@ int lcgp_plan_create(const lcgp_problem* P, void* workspace, size_t workspace_by
 
 int lcgp_plan_run(lcgp_plan* pl, void* stream) {
     if (!pl) return LCGP_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (!pl->own) {
+        LCGP_CUDA(cudaStreamCreateWithFlags(&pl->own, cudaStreamNonBlocking));
+        LCGP_CUDA(cudaEventCreateWithFlags(&pl->ev, cudaEventDisableTiming));
+    }
+    cudaStream_t st = pl->own;
+    // everything the caller queued on `stream` (constant uploads, earlier work on the workspace) comes first
+    LCGP_CUDA(cudaEventRecord(pl->ev, (cudaStream_t)stream));
+    LCGP_CUDA(cudaStreamWaitEvent(st, pl->ev, 0));
     if (!pl->exec && !pl->eager) {
-        // warm the lazily-set kernel attributes and the stream pool outside the capture
+        // first evaluation: launch by launch (this also sets the lazily-configured kernel attributes outside
+        // the capture), then capture the same sequence for the evaluations to come
         int rc = plan_enqueue(pl, st);
         if (rc) return rc;
         LCGP_CUDA(cudaStreamSynchronize(st));
@@ -489,12 +499,12 @@ int lcgp_plan_run(lcgp_plan* pl, void* stream) {
                 if (g) cudaGraphDestroy(g);
                 pl->exec = nullptr;
                 pl->eager = true;
-                (void)cudaGetLastError();   // clear the capture error; the eager path below still runs on the GPU
             }
         } else {
             pl->eager = true;
-            (void)cudaGetLastError();
         }
+        (void)cudaGetLastError();   // a refused capture leaves a sticky-looking error behind; the plan stays usable
+        return 0;                   // results of the launch-by-launch evaluation above are already on the host
     }
     if (pl->exec) {
         note_launch();   // the graph launch itself; its kernel nodes were counted when they were captured
@@ -513,6 +523,8 @@ void lcgp_plan_destroy(lcgp_plan* pl) {
     if (!pl) return;
     if (pl->exec) cudaGraphExecDestroy(pl->exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
+    if (pl->own) { cudaStreamSynchronize(pl->own); cudaStreamDestroy(pl->own); }
+    if (pl->ev) cudaEventDestroy(pl->ev);
     delete pl;
 }
 

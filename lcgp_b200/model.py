@@ -108,11 +108,9 @@ class CudaEngine:
         self.d_info = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
         self.h2d_bytes = self.h_par.numel() * 8
         self.d2h_bytes = self.out_len * 8 + q * 4
-        # launch-bound sizes (n <= 2048): evaluations replay a captured CUDA graph (lcgp_plan_*), on a stream of
-        # the engine's own because the legacy default stream cannot be captured
+        # launch-bound sizes (n <= 2048): evaluations replay a captured CUDA graph (lcgp_plan_*)
         self.use_plans = _cabi.padded(self.n) // _cabi.NB <= 16 and os.environ.get('LCGP_GRAPHS', '1') != '0'
         self._plans = {}
-        self._plan_stream = torch.cuda.Stream(device=dev) if self.use_plans else None
         self._scratch = None
 
     def _stage(self, lLmb, lLmb0, lnug, lsig_p):
@@ -159,8 +157,7 @@ class CudaEngine:
                                                self.h_out.data_ptr(), self.h_info.data_ptr(), flags, C.byref(h))
                 _cabi.check(rc, 'lcgp_plan_create')
                 plan = self._plans[flags] = h
-            self._plan_stream.wait_stream(torch.cuda.current_stream())     # constants / earlier work on the caller's stream
-            rc = self.lib.lcgp_plan_run(plan, self._plan_stream.cuda_stream)  # synchronises the plan stream
+            rc = self.lib.lcgp_plan_run(plan, _cabi.stream_ptr())   # ordered after the current stream; synchronises
         _cabi.check(rc, 'lcgp_plan_run')
 
     def plan_is_graph(self):

@@ -1,20 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_s3.log 2>&1; tail -5 gpurun_out/pytest_gpu_s3.log
-for g in 0 1; do
+for g in 0 1 1 0; do
   echo "== cfg5 LCGP_GRAPHS=$g"
-  LCGP_GRAPHS=$g timeout 600 python bench.py --config cfg5_batch 2> gpurun_out/bench_cfg5_s3_g$g.err | tee gpurun_out/bench_cfg5_s3_g$g.json | cut -c1-260
+  LCGP_GRAPHS=$g timeout 600 python bench.py --config cfg5_batch 2> gpurun_out/bench_cfg5_s3_g$g.err | tee gpurun_out/bench_cfg5_s3_g$g.json | cut -c1-200
 done
-for t in 4 16; do
+for t in 2 4 16; do
   echo "== cfg5 graphs threads=$t"
   timeout 600 python bench.py --config cfg5_batch --threads $t 2>/dev/null | cut -c1-200
-done
-for g in 0 1; do
-  echo "== cfg3 fit LCGP_GRAPHS=$g"
-  LCGP_GRAPHS=$g timeout 600 python bench.py --config cfg3_rep --no-cpu-baseline --fit-config cfg3_rep --steps 5 2>/dev/null | python -c "
-import sys, json
-for ln in sys.stdin:
-    if ln.startswith('{'):
-        j = json.loads(ln); print('ms/step', j['ms_per_step'], 'e2e', j['e2e']['value'], 'launches', j['gpu_launches'], 'fit', j['fit']['wall_s'], j['fit']['evals'], j['stages']['cholesky_frac_of_dgemm'])
-"
 done
