@@ -227,8 +227,11 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'NLL+grad evals/s', 'value': val, 'unit': 'evals/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_eval * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{args.config}: objective+gradient (oracle port of the reference CPU path)',
-                       'n': int(o.n), 'd': int(o.d), 'p': int(o.p), 'q': q},
+            # same workload string and keys as the CUDA arm's `config`
+            'config': {'workload': f'{args.config}: objective+gradient, n={int(o.n)} unique inputs, d={int(o.d)}, '
+                                   f'p={int(o.p)}, q={q}, submethod={mk["submethod"]}, init_params point',
+                       'n': int(o.n), 'd': int(o.d), 'p': int(o.p), 'q': q,
+                       'l2': 'n/a (host)', 'parallelism': f'oracle port of the reference CPU path on {threads} host threads'},
             'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))

@@ -970,7 +970,7 @@ def _fullcov_cuda(psi, gvar, sig2, ystd, device=None, chunk_bytes=4 << 30):
     n0 = int(gvar.shape[1])
     c = lambda a: a.to(dev, DT).contiguous()
     psi_d, sig_d, sv_d = c(psi), c(sig2), c(ystd)
-    step = max(1, min(n0, int(chunk_bytes // (8 * p * p))))
+    step = max(1, min(n0, int(chunk_bytes // (8 * p * p)), 1 << 19))
     out = torch.empty((n0, p, p), dtype=DT)
     with torch.cuda.device(dev):
         for s in range(0, n0, step):
