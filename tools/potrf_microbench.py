@@ -21,7 +21,7 @@ def run(npad, batch, reps=20, check=False):
         L.lcgp_potrf_batched(F.data_ptr(), npad, batch, DLb.data_ptr(), DUb.data_ptr(), None, info.data_ptr(), st)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
-    if check:
+    if check and not os.environ.get('LCGP_DIAG_MODE'):
         Lref = torch.linalg.cholesky(A[0])
         err = (torch.tril(F[0]) - Lref).abs().max().item() / Lref.abs().max().item()
         print(f'   check vs torch.linalg.cholesky: max rel err {err:.2e}  info {info.tolist()}')
@@ -33,4 +33,4 @@ def run(npad, batch, reps=20, check=False):
 import os
 CASES = [(128, 1)] if os.environ.get("DIAG_ONLY") else [tuple(int(v) for v in c.split('x')) for c in os.environ["CASES"].split(',')] if os.environ.get("CASES") else [(128, 1), (128, 8), (128, 32), (256, 1), (512, 1), (1024, 1), (1024, 8), (2048, 1), (2048, 10), (4096, 4), (8064, 1), (8064, 4)]
 for npad, batch in CASES:
-    run(npad, batch, check=(npad in (1024, 8064) and batch == 1))
+    run(npad, batch, check=(npad in (128, 1024, 8064) and batch == 1))
