@@ -110,9 +110,11 @@ void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[NSRC]) {
 // Synchronisation is split-phase (mbarriers, no CTA-wide rendezvous in the loop): the 16 owners of
 // column c+1 update that column FIRST, publish it to shared memory and arrive on ready[(c+1)&1];
 // everybody then finishes the rest of step c while the publication propagates, and waits on the
-// mbarrier only at the top of step c+1.  consumed[] (256 arrivals, made as soon as a thread has the
-// column in registers) protects the two-deep u buffer against overwriting.  The critical path per
-// column is  wait -> LDS -> reciprocal -> 8 FMAs -> STS -> arrive  on 16 threads.
+// mbarrier only at the top of step c+1.  The two-deep u buffer needs no second barrier: every warp
+// holds two owners of every column (tx = lane % 16), so ready[c] completing means every warp has
+// published column c -- in its step c-1, after the loads of that step returned (the published values
+// depend on them) -- and buffer (c+1)&1, last read in step c-1, is free when column c+1 is written in
+// step c.  The critical path per column is  wait -> LDS -> reciprocal -> 8 FMAs -> STS -> arrive.
 // ------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
 constexpr int DPITCH = NB + 1;
@@ -128,7 +130,6 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
     double* invd = pivs + NB;           // 1 / L_cc
     double* red = invd + NB;            // 8 doubles of reduction scratch, then 4 mbarriers
     const unsigned ready0 = smem_u32(red + 8);      // ready[2]
-    const unsigned cons0 = ready0 + 16;             // consumed[2]
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int bz = blockIdx.x;
@@ -136,7 +137,6 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
 
     if (tid == 0) {
         mbar_init(ready0, 16); mbar_init(ready0 + 8, 16);
-        mbar_init(cons0, DIAG_THREADS); mbar_init(cons0 + 8, DIAG_THREADS);
     }
     double reg[8][8];
 #pragma unroll
@@ -171,10 +171,12 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
             for (int i = 0; i < 8; ++i) ua[i] = ub_[ty + 16 * i];
 #pragma unroll
             for (int j = 0; j < 8; ++j) ub[j] = ub_[tx + 16 * j];
-            mbar_arrive(cons0 + 8 * buf);    // this thread no longer needs the buffer
 #pragma unroll
             for (int i = 0; i < 8; ++i) ua[i] *= ipiv;
-            const bool p_bgt = tx > cc, p_ale = ty <= cc;
+            const bool p_ale = ty <= cc;
+            // columns b <= c of group jc are finished: a zero multiplier leaves them untouched (x - u * 0 == x)
+            // instead of a predicate (and a select pair) per update
+            const double ub_c = (tx > cc) ? ub[jc] : 0.0;
             // which register column holds global column c+1 for its owners (tx == (cc+1) & 15)
             const bool own_next = (c + 1 < NB) && (tx == ((cc + 1) & 15));
             // ---- phase 1: the column group(s) that can contain column c+1: j == jc and j == jc+1
@@ -183,13 +185,11 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool lower = (i > j) || (i == j && p_low);
-                    const bool b_gt = (j > jc) || (j == jc && p_bgt);
                     const bool a_le = (i < jc) || (i == jc && p_ale);
-                    if (b_gt && (lower || a_le)) reg[i][j] -= ua[i] * ub[j];
+                    if (lower || a_le) reg[i][j] -= ua[i] * (j == jc ? ub_c : ub[j]);
                 }
             if (own_next) {
-                const int cn = c + 1, nbuf = cn & 1, nuse = cn >> 1;
-                mbar_wait(cons0 + 8 * nbuf, (nuse & 1) ^ 1);     // everyone has read the previous tenant
+                const int cn = c + 1, nbuf = cn & 1;
                 double* un = ucol + nbuf * NB;
                 if (cc < 15) {
 #pragma unroll
