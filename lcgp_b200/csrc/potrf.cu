@@ -118,17 +118,34 @@ void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[NSRC]) {
 // ------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
 constexpr int DPITCH = NB + 1;
-constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 2 * NB + NB + NB + 16);
+// The published column is stored permuted and padded: row t + 16 i at t * UP + i.  A thread's 8 values (its
+// rows ty + 16 i, its columns tx + 16 j) are then contiguous -- 4 LDS.128 instead of 8 LDS.64 for each of
+// u[a], u[b], 4 STS.128 to publish -- and the 80-byte stride keeps the quarter-warp phases conflict free.
+constexpr int UP = 10;
+constexpr int UBUF = 16 * UP;
+constexpr size_t DIAG_SMEM = sizeof(double) * (NB * DPITCH + 2 * UBUF + NB + NB + 16);
+
+// Owner thread (rows ty + 16 i) publishes val[0..7]; dg >= 0: val[dg] is the pivot (diagonal entry := 1).
+__device__ __forceinline__ void diag_publish(const double (&val)[8], int dg, double* un, double* pivs, int cn) {
+    double2* u2 = reinterpret_cast<double2*>(un);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        double v0 = val[i], v1 = val[i + 1];
+        if (i == dg) { pivs[cn] = v0; v0 = 1.0; }
+        if (i + 1 == dg) { pivs[cn] = v1; v1 = 1.0; }
+        u2[i >> 1] = make_double2(v0, v1);
+    }
+}
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet_part /* [batch][nb] */,
                   int* info /* [batch] */) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;                     // write-back staging only
-    double* ucol = sm + NB * DPITCH;    // [2][NB]
-    double* pivs = ucol + 2 * NB;       // pivots of all columns
+    double* ucol = sm + NB * DPITCH;    // [2][UBUF], 16-byte aligned (NB * DPITCH is even)
+    double* pivs = ucol + 2 * UBUF;     // pivots of all columns
     double* invd = pivs + NB;           // 1 / L_cc
-    double* red = invd + NB;            // 8 doubles of reduction scratch, then 4 mbarriers
+    double* red = invd + NB;            // 8 doubles of reduction scratch, then 2 mbarriers
     const unsigned ready0 = smem_u32(red + 8);      // ready[2]
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
@@ -149,74 +166,73 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
     const bool p_low = ty >= tx;
     __syncthreads();   // barriers initialised
     if (tx == 0) {     // publish column 0
+        double val[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int a = ty + 16 * i;
-            if (i == 0 && ty == 0) { pivs[0] = reg[0][0]; ucol[a] = 1.0; }
-            else ucol[a] = reg[i][0];
-        }
+        for (int i = 0; i < 8; ++i) val[i] = reg[i][0];
+        diag_publish(val, ty == 0 ? 0 : -1, ucol + ty * UP, pivs, 0);
         mbar_arrive(ready0);
     }
 
 #pragma unroll
     for (int jc = 0; jc < 8; ++jc) {
-        for (int cc = 0; cc < 16; ++cc) {
-            const int c = jc * 16 + cc;
-            const int buf = c & 1, use = c >> 1;
-            mbar_wait(ready0 + 8 * buf, use & 1);
-            const double* ub_ = ucol + buf * NB;
-            const double ipiv = fast_rcp(pivs[c]);
-            double ua[8], ub[8];
+        for (int cp = 0; cp < 8; ++cp) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ua[i] = ub_[ty + 16 * i];
+            for (int h = 0; h < 2; ++h) {      // unrolled by two: the buffer index c & 1 == h is static
+                const int cc = 2 * cp + h;
+                const int c = jc * 16 + cc;
+                mbar_wait(ready0 + 8 * h, cp & 1);             // tenant c >> 1 = jc * 8 + cp of buffer h
+                const double ipiv = fast_rcp(pivs[c]);
+                double ua[8], ub[8];
+                {
+                    const double2* pa = reinterpret_cast<const double2*>(ucol + h * UBUF + ty * UP);
+                    const double2* pb = reinterpret_cast<const double2*>(ucol + h * UBUF + tx * UP);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ub[j] = ub_[tx + 16 * j];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ua[i] *= ipiv;
-            const bool p_ale = ty <= cc;
-            // columns b <= c of group jc are finished: a zero multiplier leaves them untouched (x - u * 0 == x)
-            // instead of a predicate (and a select pair) per update
-            const double ub_c = (tx > cc) ? ub[jc] : 0.0;
-            // which register column holds global column c+1 for its owners (tx == (cc+1) & 15)
-            const bool own_next = (c + 1 < NB) && (tx == ((cc + 1) & 15));
-            // ---- phase 1: the column group(s) that can contain column c+1: j == jc and j == jc+1
-#pragma unroll
-            for (int j = jc; j < 8 && j <= jc + 1; ++j)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool lower = (i > j) || (i == j && p_low);
-                    const bool a_le = (i < jc) || (i == jc && p_ale);
-                    if (lower || a_le) reg[i][j] -= ua[i] * (j == jc ? ub_c : ub[j]);
-                }
-            if (own_next) {
-                const int cn = c + 1, nbuf = cn & 1;
-                double* un = ucol + nbuf * NB;
-                if (cc < 15) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int a = ty + 16 * i;
-                        if (i == jc && ty == cc + 1) { pivs[cn] = reg[i][jc]; un[a] = 1.0; }
-                        else un[a] = reg[i][jc];
-                    }
-                } else if (jc < 7) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int a = ty + 16 * i;
-                        if (i == jc + 1 && ty == 0) { pivs[cn] = reg[i][(jc + 1) & 7]; un[a] = 1.0; }
-                        else un[a] = reg[i][(jc + 1) & 7];
+                    for (int k = 0; k < 4; ++k) {
+                        const double2 qa = pa[k], qb = pb[k];
+                        ua[2 * k] = qa.x * ipiv; ua[2 * k + 1] = qa.y * ipiv;
+                        ub[2 * k] = qb.x; ub[2 * k + 1] = qb.y;
                     }
                 }
-                mbar_arrive(ready0 + 8 * nbuf);
+                const bool p_ale = ty <= cc;
+                // columns b <= c of group jc are finished: a zero multiplier leaves them untouched (x - u * 0 == x)
+                // instead of a predicate (and a select pair) per update
+                const double ub_c = (tx > cc) ? ub[jc] : 0.0;
+                // owners of column c+1: tx == (cc+1) & 15, two lanes of every warp
+                const bool own_next = (c + 1 < NB) && (tx == ((cc + 1) & 15));
+                // ---- phase 1: the column group(s) that can contain column c+1: j == jc and j == jc+1
+#pragma unroll
+                for (int j = jc; j < 8 && j <= jc + 1; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool lower = (i > j) || (i == j && p_low);
+                        const bool a_le = (i < jc) || (i == jc && p_ale);
+                        if (lower || a_le) reg[i][j] -= ua[i] * (j == jc ? ub_c : ub[j]);
+                    }
+                if (own_next) {
+                    const int cn = c + 1;
+                    double* un = ucol + (1 - h) * UBUF + ty * UP;
+                    double val[8];
+                    if (cc < 15) {      // column c+1 is in register column jc; its diagonal row is ty == cc+1, i == jc
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) val[i] = reg[i][jc];
+                        diag_publish(val, ty == cc + 1 ? jc : -1, un, pivs, cn);
+                    } else if (jc < 7) {   // first column of the next group: diagonal row ty == 0, i == jc+1
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) val[i] = reg[i][(jc + 1) & 7];
+                        diag_publish(val, ty == 0 ? jc + 1 : -1, un, pivs, cn);
+                    }
+                    mbar_arrive(ready0 + 8 * (1 - h));
+                }
+                // ---- phase 2: all remaining column groups
+#pragma unroll
+                for (int j = jc + 2; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool lower = (i > j) || (i == j && p_low);
+                        const bool a_le = (i < jc) || (i == jc && p_ale);
+                        if (lower || a_le) reg[i][j] -= ua[i] * ub[j];
+                    }
             }
-            // ---- phase 2: all remaining column groups
-#pragma unroll
-            for (int j = jc + 2; j < 8; ++j)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool lower = (i > j) || (i == j && p_low);
-                    const bool a_le = (i < jc) || (i == jc && p_ale);
-                    if (lower || a_le) reg[i][j] -= ua[i] * ub[j];
-                }
         }
     }
     __syncthreads();
