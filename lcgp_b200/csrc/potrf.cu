@@ -284,7 +284,7 @@ static cudaError_t diag_configure() {
 // update with K = 128 pw, which halves / quarters the C read-modify-write traffic and the number of
 // pipeline fills per flop compared with a rank-128 update per block column.
 //
-// Look-ahead (la.panel != nullptr): the serial panel chain (column update -> 58 us diagonal kernel -> panel
+// Look-ahead (la.panel != nullptr): the serial panel chain (column update -> ~50 us diagonal kernel -> panel
 // solve, ~150 us per block column) runs on the high-priority stream la.panel; the trailing update of panel k
 // is split into the NEXT panel's block columns (on la.panel, so that panel k+1 can start at once) and the
 // bulk (on `stream`), and panel k+1 is factored while the bulk of update k is still running:
