@@ -155,6 +155,14 @@ int lcgp_prep_row_select(const double* Y, const double* center, int32_t p, int32
 int lcgp_prep_standardize(const double* Y, const double* center, const double* spread, const double* r, int32_t p,
                           int32_t n, double* Ys, double* YR, double* w, void* stream);
 
+/* Gradient of this rank's part of the objective with respect to its columns of the latent basis phi (p x q_loc),
+ * diag_D treated as the function d_k = sum_j phi_jk^2 of it.  The reference keeps phi constant (lcgp.py:164), so this
+ * has no reference counterpart; it exists for callers that train the basis (north-star "shared parameters").
+ * Valid right after lcgp_nll_grad with the gradient bit at the same parameters (reads the factor, m_k and Z from the
+ * workspace).  lsigma2_p, g_phi: device pointers. */
+int lcgp_grad_phi(const lcgp_problem* prob, const double* lsigma2_p, void* workspace, size_t workspace_bytes,
+                  double* g_phi, void* stream);
+
 /* Copies alpha (CinvMs) and m (mks), each q_loc x n, out of the workspace. */
 int lcgp_get_aux(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
                  void* stream);

@@ -566,6 +566,18 @@ int lcgp_prep_standardize(const double* Y, const double* center, const double* s
     return cuda_rc(prep_standardize(Y, center, spread, r, p, n, Ys, YR, w, (cudaStream_t)stream));
 }
 
+int lcgp_grad_phi(const lcgp_problem* P, const double* lsigma2_p, void* workspace, size_t workspace_bytes, double* g_phi,
+                  void* stream) {
+    int rc = check_problem(P);
+    if (rc) return rc;
+    if (!lsigma2_p || !workspace || !g_phi) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
+    // scratch: the GEMV partial-sum area, free once lcgp_nll_grad has finished
+    return cuda_rc(grad_phi(view_of(w), P->n, P->p, P->q_loc, P->scale, P->sr, w.mk, lsigma2_p, P->t, P->phi, P->D, w.Z,
+                            w.gemv_part, g_phi, (cudaStream_t)stream));
+}
+
 int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
                  void* stream) {
     int rc = check_problem(P);

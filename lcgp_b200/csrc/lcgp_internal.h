@@ -56,6 +56,10 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
                           double* g_ell, double* g_s0, double* g_lnug, cudaEvent_t ev_before, cudaEvent_t ev_after,
                           cudaStream_t stream);
 
+cudaError_t grad_phi(const FactorView& v, int n, int p, int q_loc, double scale, const double* sr, const double* mk,
+                     const double* lsig, const double* t, const double* phi, const double* D, const double* Z,
+                     double* part /* 2 * q_loc * nb scratch */, double* g_phi /* p x q_loc */, cudaStream_t stream);
+
 // predict.cu
 cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,
                             const double* atil, const double* x0s, int n0, int same, double* scratch,

@@ -287,4 +287,64 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
     return cudaGetLastError();
 }
 
+// ---- gradient with respect to the latent basis (no counterpart in the reference, where phi is a
+// constant): per latent k it needs tr A_k^{-1} = sum_{i<n} sum_{kk>=i} U[i][kk]^2 and sum_i r_i m_ki^2.
+// One CTA per (row block, latent) streams its 128 rows of U once (HBM bound: 8 * np^2 / 2 bytes per latent).
+__global__ void __launch_bounds__(256)
+trace_part_kernel(FactorView v, int n, const double* __restrict__ sr, const double* __restrict__ mk,
+                  double* __restrict__ part /* [q_loc][nb][2] */) {
+    __shared__ double red[8];
+    const int rb = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
+    const double* F = v.F + (size_t)k * v.fstride;
+    const double* DU = v.DU + (size_t)k * v.dstride + (size_t)rb * NB * NB;
+    double acc = 0.0;
+    const int rows = min(NB, n - rb * NB);           // rows i < n of this block (pad rows are the identity)
+    for (int idx = tid; idx < rows * NB; idx += 256) {   // diagonal block: dense DU (zeros below the diagonal)
+        const double u = DU[idx];
+        acc += u * u;
+    }
+    for (int kb = rb + 1; kb < v.nb; ++kb)
+        for (int idx = tid; idx < rows * NB; idx += 256) {
+            const int r = idx >> 7, c = idx & (NB - 1);
+            const double u = F[(size_t)(rb * NB + r) * v.np + (size_t)kb * NB + c];
+            acc += u * u;
+        }
+    acc = block_sum(acc, red);
+    double rm = 0.0;
+    if (tid < rows) {
+        const int i = rb * NB + tid;
+        const double m = mk[(size_t)k * v.np + i], s = sr[i];
+        rm = s * s * m * m;
+    }
+    rm = block_sum(rm, red);
+    if (tid == 0) {
+        part[((size_t)k * v.nb + rb) * 2] = acc;
+        part[((size_t)k * v.nb + rb) * 2 + 1] = rm;
+    }
+}
+
+// g_phi[j][k] = scale * ( -s_j Z[j][k] + 2 phi[j][k] dT_k/dd_k ),  dT_k/dd_k = (n - tr A_k^-1) / (2 d_k) + 1/2 sum_i r_i m_ki^2
+__global__ void phi_grad_kernel(int n, int p, int q, int nb, double scale, const double* __restrict__ lsig,
+                                const double* __restrict__ t, const double* __restrict__ phi, const double* __restrict__ D,
+                                const double* __restrict__ Z, const double* __restrict__ part, double* __restrict__ g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p * q) return;
+    const int j = idx / q, k = idx % q;
+    double tr = 0.0, rm = 0.0;
+    for (int b = 0; b < nb; ++b) { tr += part[((size_t)k * nb + b) * 2]; rm += part[((size_t)k * nb + b) * 2 + 1]; }
+    const double dTd = ((double)n - tr) / (2.0 * D[k]) + 0.5 * rm;
+    const double sj = exp(-0.5 * lsig[j]) * t[j];
+    g[idx] = scale * (-sj * Z[idx] + 2.0 * phi[idx] * dTd);
+}
+
+cudaError_t grad_phi(const FactorView& v, int n, int p, int q_loc, double scale, const double* sr, const double* mk,
+                     const double* lsig, const double* t, const double* phi, const double* D, const double* Z,
+                     double* part, double* g_phi, cudaStream_t stream) {
+    note_launch(); trace_part_kernel<<<dim3(v.nb, q_loc), 256, 0, stream>>>(v, n, sr, mk, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    note_launch(); phi_grad_kernel<<<(p * q_loc + 255) / 256, 256, 0, stream>>>(n, p, q_loc, v.nb, scale, lsig, t, phi, D, Z, part, g_phi);
+    return cudaGetLastError();
+}
+
 }  // namespace lcgp

@@ -211,6 +211,16 @@ class CudaEngine:
         _cabi.check(rc, 'lcgp_predict')
         return ghat, gvar
 
+    def grad_phi(self, lsig_p):
+        """d objective / d phi[:, local latents] (p x q_loc, device) from the state the last evaluate(with_grad=True) left."""
+        with torch.cuda.device(self.device):
+            ls = lsig_p.to(self.device, DT).contiguous()
+            g = torch.empty((self.p, self.q_loc), dtype=DT, device=self.device)
+            rc = self.lib.lcgp_grad_phi(self.prob, ls.data_ptr(), self.ws.data_ptr(), self.ws_bytes, g.data_ptr(),
+                                        _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_grad_phi')
+        return g
+
     def aux(self):
         a = torch.empty((self.q_loc, self.n), dtype=DT, device=self.device)
         m = torch.empty((self.q_loc, self.n), dtype=DT, device=self.device)
@@ -751,6 +761,24 @@ class LCGP:
         val = self.loss()
         val.backward()
         return float(val.detach()), torch.cat([v.grad.reshape(-1) for v in tv]).numpy().copy()
+
+    def grad_phi(self):
+        """Gradient of loss() with respect to the latent basis phi (p x q), with diag_D following phi
+        (d_k = sum_j phi_jk^2).  The reference keeps phi constant (lcgp.py:164); this serves callers that train the
+        basis.  Sharded like the objective: each rank computes its latents' columns, one all-reduce gathers them."""
+        lLmb, lLmb0, lsig_p, lnug = self.get_param()
+        self._evaluate(lLmb, lLmb0, lsig_p, lnug, need_grad=True)
+        q, p = int(self.q), int(self.p)
+        eng = self.engine
+        loc = eng.grad_phi(lsig_p) if eng is not False else None
+        if self._world == 1:
+            return loc.cpu()
+        dev = self._collective_device()
+        full = torch.zeros((p, q), dtype=DT, device=dev)
+        if loc is not None:
+            full[:, self._local_idx.to(dev)] = loc.to(dev)
+        torch.distributed.all_reduce(full)
+        return full.cpu()
 
     def _flat_get(self):
         return torch.cat([v.detach().reshape(-1) for v in self.trainable_variables]).numpy().copy()

@@ -349,6 +349,73 @@ def test_row_select_is_the_nearest_rank_percentile(m):
     assert torch.equal(out.cpu(), torch.sort(torch.abs(Y - want[:, None]), dim=1).values[:, k])
 
 
+@pytest.mark.parametrize('sub', ['rep', 'full'])
+def test_gradient_wrt_latent_basis_matches_oracle_autograd(sub):
+    """lcgp_grad_phi (no reference counterpart) against autograd through the oracle's objective with
+    phi a leaf and diag_D = sum_j phi_jk^2 a function of it; n spans several 128-blocks with a ragged last one."""
+    if sub == 'rep':
+        x, y, _ = make_ragged_rep_data(seed=17, n_unique=300, p=6, d=3)
+    else:
+        x, y = make_full_data(seed=18, n=290, p=5, d=2)
+    m, o = _pair(x, y, q=3, submethod=sub)
+    move_params(m, o, seed=5)
+    g = m.grad_phi()
+    phi = o.phi.clone().requires_grad_(True)
+    o.phi, o.diag_D = phi, (phi ** 2).sum(dim=0)
+    o.loss().backward()
+    assert g.shape == phi.shape
+    assert rel(g, phi.grad) < GRAD_TOL, rel(g, phi.grad)
+
+
+def test_auxiliary_kernels_respect_their_output_bounds():
+    """Guard bands around every output of lcgp_predict_fullcov and the lcgp_prep_* kernels (ragged sizes: p, n0,
+    n not multiples of any tile) stay untouched (compute-sanitizer is not available on this pool)."""
+    L = _cabi.lib()
+    dev, G, SENT = torch.device('cuda'), 257, -12345.678
+    st = _cabi.stream_ptr()
+
+    def guarded(numel):
+        buf = torch.full((numel + 2 * G,), SENT, dtype=torch.float64, device=dev)
+        return buf, buf[G:G + numel]
+
+    def intact(buf, numel):
+        return bool((buf[:G] == SENT).all()) and bool((buf[G + numel:] == SENT).all())
+
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for q, p, n0 in [(5, 131, 19), (3, 7, 33), (70, 129, 3)]:
+        psi = torch.randn(q, p, dtype=torch.float64, device=dev, generator=g)
+        gv = torch.rand(q, n0, dtype=torch.float64, device=dev, generator=g)
+        s2 = torch.rand(p, dtype=torch.float64, device=dev, generator=g)
+        sv = torch.rand(p, dtype=torch.float64, device=dev, generator=g) + 0.5
+        buf, out = guarded(n0 * p * p)
+        _cabi.check(L.lcgp_predict_fullcov(psi.data_ptr(), gv.data_ptr(), s2.data_ptr(), sv.data_ptr(), q, p, n0,
+                                           out.data_ptr(), st), 'fullcov')
+        torch.cuda.synchronize()
+        assert intact(buf, n0 * p * p) and bool(torch.isfinite(out).all()) and not bool((out == SENT).any())
+    p, N, n = 9, 1003, 377
+    rng = np.random.default_rng(0)
+    inv = np.concatenate([np.arange(n), rng.integers(0, n, N - n)]); rng.shuffle(inv)
+    order = torch.as_tensor(np.argsort(inv, kind='stable').astype(np.int32)).to(dev)
+    off = torch.as_tensor(np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=n))]).astype(np.int32)).to(dev)
+    y = torch.randn(p, N, dtype=torch.float64, device=dev, generator=g)
+    bybar, ybar = guarded(p * n)
+    _cabi.check(L.lcgp_prep_segment_mean(y.data_ptr(), order.data_ptr(), off.data_ptr(), p, N, n, ybar.data_ptr(), st), 'segmean')
+    bc, c = guarded(p)
+    _cabi.check(L.lcgp_prep_row_select(ybar.data_ptr(), None, p, n, n // 2, c.data_ptr(), st), 'select')
+    bs, sp = guarded(p)
+    _cabi.check(L.lcgp_prep_row_select(ybar.data_ptr(), c.data_ptr(), p, n, n // 2, sp.data_ptr(), st), 'select')
+    r = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 1.0
+    bys, ys = guarded(p * n); byr, yr = guarded(p * n); bw, w = guarded(p)
+    _cabi.check(L.lcgp_prep_standardize(ybar.data_ptr(), c.data_ptr(), sp.data_ptr(), r.data_ptr(), p, n, ys.data_ptr(),
+                                        yr.data_ptr(), w.data_ptr(), st), 'standardize')
+    torch.cuda.synchronize()
+    for b, m in ((bybar, p * n), (bc, p), (bs, p), (bys, p * n), (byr, p * n), (bw, p)):
+        assert intact(b, m)
+    Yb = ybar.view(p, n)
+    assert torch.equal(c, torch.sort(Yb, dim=1).values[:, n // 2])
+    assert torch.allclose(w, ((Yb - c[:, None]) / sp[:, None]) ** 2 @ r, rtol=1e-13)
+
+
 # ---------------------------------------------------------------- a10: fit
 @pytest.mark.parametrize('optimizer', ['L-BFGS-B', 'torch-lbfgs'])
 def test_fit_matches_oracle_under_shared_optimizer(optimizer):
