@@ -38,16 +38,14 @@ static bool lookahead_on() { static const int v = env_int("LCGP_LOOKAHEAD", 1, 0
 // Side streams + fork/join events, created on first use for the current device.  The library
 // still allocates no device memory; these are the only objects that outlive a call.
 struct SidePool {
-    int device = -1;
+    bool ready = false;
     cudaStream_t s[MAX_GROUPS];
     cudaStream_t hp[MAX_GROUPS];                     // high-priority panel streams (Cholesky look-ahead)
     cudaEvent_t fork, join[MAX_GROUPS], evp[MAX_GROUPS], evb[MAX_GROUPS];
     std::mutex mu;
     cudaError_t ensure() {
-        int dev;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (dev == device) return cudaSuccess;
+        if (ready) return cudaSuccess;
+        cudaError_t e;
         int least = 0, greatest = 0;
         if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return e;
         for (int i = 0; i < MAX_GROUPS; ++i) {
@@ -58,11 +56,17 @@ struct SidePool {
             if ((e = cudaEventCreateWithFlags(&evb[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
         if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-        device = dev;
+        ready = true;
         return cudaSuccess;
     }
 };
-static SidePool& side_pool() { static SidePool p; return p; }
+// one pool per device (streams and events belong to the device that was current when they were created)
+static SidePool& side_pool() {
+    static SidePool pools[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+    return pools[dev];
+}
 
 // Runs f(first_latent, count, stream, group) for G contiguous groups of the q latents, each on its own
 // side stream, between a fork from and a join back into `main`.  The pool stays locked while work that

@@ -5,6 +5,8 @@
 // The output write is the algorithmic traffic (8 n0 p^2 bytes); with q = 32 the 2 q flop per element are also
 // close to the FP64 tensor rate per SM, so the products run on DMMA (m8n8k4) from shared-memory tiles of
 // psi^T that stay resident while the CTA walks over its test points.
+#include <atomic>
+
 #include "common.cuh"
 #include "lcgp_internal.h"
 
@@ -119,14 +121,14 @@ fullcov_kernel(const double* __restrict__ psi, const double* __restrict__ gvar, 
 
 cudaError_t launch_fullcov(const double* psi, const double* gvar, const double* sig2, const double* sv, int q, int p,
                            int n0, double* out, cudaStream_t stream) {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (!configured[dev]) {
+    if (!configured[dev].load(std::memory_order_acquire)) {   // racing first calls both set the attribute: harmless
         cudaError_t e = cudaFuncSetAttribute(fullcov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     const int tiles = (p + NB - 1) / NB;
     // test points per CTA: as many as keep >= ~4 CTAs per SM in flight (the psi tiles are loaded once per CTA)

@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace lcgp {
@@ -353,20 +355,20 @@ inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p
                                int max_kblocks = 1 << 20) {
     const int dev = (ctx.device >= 0 && ctx.device < MAX_DEVICES) ? ctx.device : 0;
     if (ctx.tma && max_kblocks >= gemm_tma_min_kblocks()) {
-        static bool configured[MAX_DEVICES] = {};
-        if (!configured[dev]) {
+        static std::atomic<bool> configured[MAX_DEVICES];
+        if (!configured[dev].load(std::memory_order_acquire)) {   // racing first calls both set the attribute: harmless
             cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_TMA);
             if (e != cudaSuccess) return e;
-            configured[dev] = true;
+            configured[dev].store(true, std::memory_order_release);
         }
         note_launch(); gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
     } else {
         constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
-        static bool configured[MAX_DEVICES] = {};
-        if (!configured[dev]) {
+        static std::atomic<bool> configured[MAX_DEVICES];
+        if (!configured[dev].load(std::memory_order_acquire)) {   // racing first calls both set the attribute: harmless
             cudaError_t e = cudaFuncSetAttribute(gemm_dmma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured[dev] = true;
+            configured[dev].store(true, std::memory_order_release);
         }
         note_launch(); gemm_dmma_kernel<Job><<<grid, GEMM_THREADS, smem, stream>>>(p, ctx.srcs);
     }

@@ -4,6 +4,8 @@
 //                          TrsmJob      : P = A[jb+1:, jb] * DL^T                 (DMMA GEMM)
 //                          SyrkJob      : A[I][J] -= P_I P_J^T (panel-column and trailing updates, DMMA GEMM)
 //   TRTRI: bottom-up binary merges of already-inverted diagonal ranges, two DMMA GEMMs per level.
+#include <atomic>
+
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
 
@@ -268,13 +270,13 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
 }
 
 static cudaError_t diag_configure() {
-    static bool done[MAX_DEVICES] = {};
+    static std::atomic<bool> done[MAX_DEVICES];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= MAX_DEVICES) dev = 0;
-    if (done[dev]) return cudaSuccess;
+    if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
-    if (e == cudaSuccess) done[dev] = true;
+    if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
     return e;
 }
 
