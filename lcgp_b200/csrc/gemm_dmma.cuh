@@ -41,6 +41,7 @@ struct GemmSrcs {                         // pointer view (batch element b start
 struct GemmMaps {                         // TMA view: 3-D maps (column, row, batch) of the same buffers
     CUtensorMap km[NSRC];                 // box 16 x 128 x 1  (K-major operand: 16 k-columns of 128 rows)
     CUtensorMap nm[2];                    // box 16 x 32 x 1   (N-major operand from SRC_F / SRC_DU)
+    CUtensorMap km64;                     // box 16 x 64 x 1   (operand A of half-tile launches, from SRC_F)
 };
 
 // Storage convention for one latent's factor buffer F (np x np, row-major, np % NB == 0):
@@ -61,6 +62,7 @@ struct FactorView {
 // cp.async engine: natural m8n8k4 layout.  lane = 4 g + t : a = A[g][t], b = B[t][g], d = D[g][2t, 2t+1]
 struct WarpCoord {
     static constexpr bool kPairs = true;   // a lane's two accumulator columns are adjacent
+    static constexpr int kMI = 8;          // 8-row accumulator groups per warp (warp tile 64 x 32)
     int wm, wn, g, t;
     __device__ __forceinline__ WarpCoord() {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,10 +83,14 @@ struct WarpCoord {
 // of an MMA over two 16-byte chunk groups of a 16-wide box: conflict free AND adjacent.
 __device__ __forceinline__ int perm8(int g) { return ((g & 3) << 1) | (g >> 2); }
 
-template <bool BNMAJOR>
+// MT = rows of the CTA tile: NB (warp tile 64 x 32) or NB / 2 (warp tile 32 x 32; blockIdx.z picks the upper or
+// lower half of the 128-row tile the Job describes -- used for launches with fewer tiles than SMs, where
+// halving the work per CTA halves the latency of a kernel that sits on a serial chain).
+template <bool BNMAJOR, int MT = NB>
 struct TmaCoord {
     static constexpr bool kPairs = true;
-    int wm, wn, g, t, pg;
+    static constexpr int kMI = MT / 16;
+    int wm, wn, g, t, pg, moff;
     __device__ __forceinline__ TmaCoord() {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         wm = warp >> 2;
@@ -92,8 +98,9 @@ struct TmaCoord {
         g = lane >> 2;
         t = lane & 3;
         pg = perm8(g);
+        moff = (MT == NB) ? 0 : (int)blockIdx.z * MT;
     }
-    __device__ __forceinline__ int row(int mi) const { return wm * 64 + mi * 8 + pg; }
+    __device__ __forceinline__ int row(int mi) const { return moff + wm * (MT / 2) + mi * 8 + pg; }
     __device__ __forceinline__ int col(int ni, int e) const {
         if (BNMAJOR) return wn * 32 + 16 * (ni >> 1) + 4 * (ni & 1) + ((t & 1) << 3) + (t & 2) + e;   // {0,8,2,10}[t]
         return wn * 32 + ni * 8 + 2 * t + e;
@@ -202,9 +209,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const typena
 // TMA engine
 // ---------------------------------------------------------------------------------------------
 constexpr int TMA_BOX_K = 16;                                  // doubles per swizzled 128-byte row
-constexpr int TMA_OPERAND_BYTES = NB * BK * 8;                 // 32 KB per operand per stage
-constexpr int TMA_STAGE_BYTES = 2 * TMA_OPERAND_BYTES;         // 64 KB
-constexpr size_t GEMM_SMEM_TMA = (size_t)STAGES * TMA_STAGE_BYTES + 64 + 1024;   // + mbarriers + alignment slack
+constexpr int TMA_B_BYTES = NB * BK * 8;                       // 32 KB: operand B per stage
+template <int MT> struct TmaShape {
+    static constexpr int kABytes = MT * BK * 8;                // operand A per stage (32 KB, or 16 KB for half tiles)
+    static constexpr int kStageBytes = kABytes + TMA_B_BYTES;
+    static constexpr size_t kSmem = (size_t)STAGES * kStageBytes + 64 + 1024;   // + mbarriers + alignment slack
+};
+constexpr size_t GEMM_SMEM_TMA = TmaShape<NB>::kSmem;
 
 __device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
@@ -218,19 +229,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // K-major operand tile in shared memory: 2 boxes (k 0..15 | 16..31) of [128 rows][128 B], chunk ^= row % 8.
 // N-major operand tile: 8 boxes (16 n each) of [32 k rows][128 B].
-template <bool BNMAJOR>
+template <bool BNMAJOR, int MT>
 __device__ __forceinline__ void tma_compute_stage(const unsigned char* __restrict__ As, const unsigned char* __restrict__ Bs,
-                                                  double (&acc)[8][4][2], const TmaCoord<BNMAJOR>& wc) {
-    const int arow = (wc.wm * 64 + wc.pg) * 128;      // + mi * 1024
+                                                  double (&acc)[MT / 16][4][2], const TmaCoord<BNMAJOR, MT>& wc) {
+    constexpr int MI = MT / 16;
+    const int arow = (wc.wm * (MT / 2) + wc.pg) * 128;   // + mi * 1024
     const int brow = (wc.wn * 32 + wc.g) * 128;       // K-major B (natural row order): + ni * 1024
     // N-major B: column c = nperm(ni & 1, g) inside box (wn * 2 + ni / 2)
     const int cn0 = (wc.g & 1) + ((wc.g & 2) << 2) + ((wc.g & 4) >> 1);
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-        double a[8], b[4];
-        const int akoff = (kk >> 2) * (NB * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.pg) << 4) + ((wc.t & 1) << 3);
+        double a[MI], b[4];
+        const int akoff = (kk >> 2) * (MT * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.pg) << 4) + ((wc.t & 1) << 3);
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) a[mi] = *reinterpret_cast<const double*>(As + arow + mi * 1024 + akoff);
+        for (int mi = 0; mi < MI; ++mi) a[mi] = *reinterpret_cast<const double*>(As + arow + mi * 1024 + akoff);
         if (!BNMAJOR) {
             const int bkoff = (kk >> 2) * (NB * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.g) << 4) + ((wc.t & 1) << 3);
 #pragma unroll
@@ -245,24 +257,26 @@ __device__ __forceinline__ void tma_compute_stage(const unsigned char* __restric
             }
         }
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 
-template <class Job>
+template <class Job, int MT = NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_constant__ GemmMaps maps) {
+    typedef TmaShape<MT> Shape;
+    const int moff = (MT == NB) ? 0 : (int)blockIdx.z * MT;   // half tiles: rows [moff, moff + MT) of the Job's 128-row tile
     extern __shared__ unsigned char smem_raw[];
     Job job;
     if (!job.init(p)) return;   // uniform over the CTA
     unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms are 1 KB
     const unsigned sm_u = smem_u32(sm);
-    const unsigned full0 = sm_u + STAGES * TMA_STAGE_BYTES, empty0 = full0 + 8 * STAGES;
+    const unsigned full0 = sm_u + STAGES * Shape::kStageBytes, empty0 = full0 + 8 * STAGES;
     if (threadIdx.x == 32) {   // hide the first descriptor fetches behind the barrier set-up
         const TileRef ra = job.a_ref(p, job.kb0), rb = job.b_ref(p, job.kb0);
-        tma_prefetch_desc(&maps.km[ra.src]);
+        tma_prefetch_desc(MT == NB ? &maps.km[ra.src] : &maps.km64);
         tma_prefetch_desc(Job::kBNMajor ? &maps.nm[rb.src == SRC_F ? 0 : 1] : &maps.km[rb.src]);
     }
     if (threadIdx.x == 0) {
@@ -281,15 +295,16 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
     auto produce = [&](int nxt, int slot, int use) {
         if (lane == 0) {
             mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);   // passes at once for the first fill
-            mbar_arrive_expect_tx(full0 + 8 * slot, TMA_STAGE_BYTES);
+            mbar_arrive_expect_tx(full0 + 8 * slot, Shape::kStageBytes);
             const int kb = job.kb0 + nxt / KSTEPS, ks = nxt % KSTEPS;
             const TileRef ra = job.a_ref(p, kb), rb = job.b_ref(p, kb);
-            const unsigned dA = sm_u + slot * TMA_STAGE_BYTES, dB = dA + TMA_OPERAND_BYTES;
+            const unsigned dA = sm_u + slot * Shape::kStageBytes, dB = dA + Shape::kABytes;
+            const CUtensorMap* ma = (MT == NB) ? &maps.km[ra.src] : &maps.km64;   // half tiles read operand A from F only
             const unsigned fb = full0 + 8 * slot;
             const int bz = blockIdx.y;
 #pragma unroll
             for (int h = 0; h < BK / TMA_BOX_K; ++h)
-                tma_load_3d(dA + h * (NB * 128), &maps.km[ra.src], ra.col + ks * BK + h * TMA_BOX_K, ra.row, bz, fb);
+                tma_load_3d(dA + h * (MT * 128), ma, ra.col + ks * BK + h * TMA_BOX_K, ra.row + moff, bz, fb);
             if (!Job::kBNMajor) {
 #pragma unroll
                 for (int h = 0; h < BK / TMA_BOX_K; ++h)
@@ -309,10 +324,10 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
             if (s < niter) produce(s, s, 0);
     }
 
-    TmaCoord<Job::kBNMajor> wc;
-    double acc[8][4][2];
+    TmaCoord<Job::kBNMajor, MT> wc;
+    double acc[MT / 16][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MT / 16; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
@@ -322,7 +337,7 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
         const int nxt = it + STAGES - 1;
         if (nxt < niter && warp == (it & 7)) produce(nxt, nslot, nuse);   // the MMA warps take turns as producer
         mbar_wait(full0 + 8 * st, ph);
-        tma_compute_stage<Job::kBNMajor>(sm + st * TMA_STAGE_BYTES, sm + st * TMA_STAGE_BYTES + TMA_OPERAND_BYTES, acc, wc);
+        tma_compute_stage<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes, acc, wc);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * st);
         if (++st == STAGES) { st = 0; ph ^= 1; }
@@ -349,20 +364,23 @@ int gemm_tma_min_kblocks();   // launches whose longest K run is shorter use the
 // rows[] = rows per batch element of each source (0 = source unused).
 cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSRC], int batch);
 
-// max_kblocks: length (in 128-blocks) of the longest K run any tile of this launch has
-template <class Job>
+// max_kblocks: length (in 128-blocks) of the longest K run any tile of this launch has.
+// MT = NB / 2 (TMA engine only, operand A from SRC_F, grid.z = 2): each 128-row tile is computed by two CTAs.
+template <class Job, int MT = NB>
 inline cudaError_t gemm_launch(const GemmCtx& ctx, const typename Job::Params& p, dim3 grid, cudaStream_t stream,
                                int max_kblocks = 1 << 20) {
     const int dev = (ctx.device >= 0 && ctx.device < MAX_DEVICES) ? ctx.device : 0;
-    if (ctx.tma && max_kblocks >= gemm_tma_min_kblocks()) {
+    if (ctx.tma && (MT != NB || max_kblocks >= gemm_tma_min_kblocks())) {
         static std::atomic<bool> configured[MAX_DEVICES];
         if (!configured[dev].load(std::memory_order_acquire)) {   // racing first calls both set the attribute: harmless
-            cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<Job>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_TMA);
+            cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<Job, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)TmaShape<MT>::kSmem);
             if (e != cudaSuccess) return e;
             configured[dev].store(true, std::memory_order_release);
         }
-        note_launch(); gemm_tma_kernel<Job><<<grid, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(p, ctx.maps);
+        note_launch(); gemm_tma_kernel<Job, MT><<<grid, GEMM_THREADS, TmaShape<MT>::kSmem, stream>>>(p, ctx.maps);
     } else {
+        if (MT != NB) return cudaErrorNotSupported;   // half tiles exist for the TMA engine only
         constexpr size_t smem = Job::kBNMajor ? GEMM_SMEM_NMAJOR : GEMM_SMEM_KMAJOR;
         static std::atomic<bool> configured[MAX_DEVICES];
         if (!configured[dev].load(std::memory_order_acquire)) {   // racing first calls both set the attribute: harmless
@@ -423,10 +441,10 @@ struct SyrkJob {
     __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_F, I * NB, kb * NB}; }
     __device__ TileRef b_ref(const Params&, int kb) const { return TileRef{SRC_F, J * NB, kb * NB}; }
     template <class Coord>
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
+    __device__ void epilogue(const Params& p, double (&acc)[Coord::kMI][4][2], double*, const Coord& wc) const {
         double* C = base + (size_t)I * NB * p.v.np + (size_t)J * NB;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < Coord::kMI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
                 double* q = C + (size_t)wc.row(mi) * p.v.np;
@@ -461,10 +479,10 @@ struct TrsmJob {
     __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_F, I * NB, kb * NB}; }
     __device__ TileRef b_ref(const Params& p, int) const { return TileRef{SRC_DL, p.jb * NB, 0}; }   // B[n=c][k] = Linv[c][k]
     template <class Coord>
-    __device__ void epilogue(const Params& p, double (&acc)[8][4][2], double*, const Coord& wc) const {
+    __device__ void epilogue(const Params& p, double (&acc)[Coord::kMI][4][2], double*, const Coord& wc) const {
         double* C = base + (size_t)I * NB * p.v.np + (size_t)p.jb * NB;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < Coord::kMI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) store_pair(C, p.v.np, wc, mi, ni, acc[mi][ni][0], acc[mi][ni][1]);
     }

@@ -33,6 +33,10 @@ static int env_clamped(const char* name, int dflt, int lo, int hi) {
 static int potrf_tail_n() { static const int v = env_clamped("LCGP_TAIL_N", 24, 0, 1 << 20); return v; }
 static int potrf_tail_w() { static const int v = env_clamped("LCGP_TAIL_W", 4, 1, 16); return v; }
 constexpr int LCGP_MAX_PANELS = 4096;
+// LCGP_HALF_TILES: panel kernels (column update, solve) with at most this many 128 x 128 tiles are launched as twice
+// as many 64 x 128 tiles: they sit on the serial panel chain and leave SMs idle anyway, so halving the work per CTA
+// halves their latency.  0 = never.
+static int half_tile_limit() { static const int v = env_clamped("LCGP_HALF_TILES", 74, 0, 1 << 20); return v; }
 
 int gemm_tma_min_kblocks() {
     static const int v = [] {
@@ -85,6 +89,10 @@ cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSR
         if (i == SRC_F || i == SRC_DU) {
             e = encode_map(&ctx.maps.nm[i == SRC_F ? 0 : 1], srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i],
                            srcs.bstride[i], BK);
+            if (e != cudaSuccess) return e;
+        }
+        if (i == SRC_F) {   // half-tile launches: operand A boxes of 64 rows
+            e = encode_map(&ctx.maps.km64, srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB / 2);
             if (e != cudaSuccess) return e;
         }
     }
@@ -332,7 +340,10 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
         for (int j = j0; j < j1; ++j) {
             if (j > j0) {
                 SyrkJob::Params cp{v, j0, j, 0, j, 0};
-                e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), ps, j - j0);
+                if (ctx.tma && (v.nb - j) * batch <= half_tile_limit())
+                    e = gemm_launch<SyrkJob, NB / 2>(ctx, cp, dim3(v.nb - j, batch, 2), ps, j - j0);
+                else
+                    e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), ps, j - j0);
                 if (e != cudaSuccess) return e;
             }
             note_launch(); potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, ps>>>(v, DLw, DUw, j, logdet_part, info);
@@ -341,7 +352,10 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
             const int T = v.nb - j - 1;
             if (T > 0) {
                 TrsmJob::Params tp{v, j};
-                e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), ps, 1);
+                if (ctx.tma && T * batch <= half_tile_limit())
+                    e = gemm_launch<TrsmJob, NB / 2>(ctx, tp, dim3(T, batch, 2), ps, 1);
+                else
+                    e = gemm_launch<TrsmJob>(ctx, tp, dim3(T, batch, 1), ps, 1);
                 if (e != cudaSuccess) return e;
             }
         }
