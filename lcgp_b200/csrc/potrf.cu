@@ -361,9 +361,15 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
         }
         const int T = v.nb - j1;
         if (T <= 0) break;
+        // trailing updates with few tiles (the tail of every factorisation) are on the chain too: half tiles
+        auto syrk = [&](const SyrkJob::Params& sp, int tiles, cudaStream_t st) {
+            if (ctx.tma && tiles * batch <= half_tile_limit())
+                return gemm_launch<SyrkJob, NB / 2>(ctx, sp, dim3(tiles, batch, 2), st, j1 - j0);
+            return gemm_launch<SyrkJob>(ctx, sp, dim3(tiles, batch, 1), st, j1 - j0);
+        };
         if (!look) {
             SyrkJob::Params sp{v, j0, j1, j1, -1, 0};
-            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T * (T + 1) / 2, batch, 1), stream, j1 - j0);
+            e = syrk(sp, T * (T + 1) / 2, stream);
             if (e != cudaSuccess) return e;
             continue;
         }
@@ -374,13 +380,13 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
             bulk_pending = false;
         }
         SyrkJob::Params lp{v, j0, j1, j1, -2, j2};
-        e = gemm_launch<SyrkJob>(ctx, lp, dim3((j2 - j1) * T, batch, 1), ps, j1 - j0);
+        e = syrk(lp, (j2 - j1) * T, ps);
         if (e != cudaSuccess) return e;
         const int T2 = v.nb - j2;
         if (T2 > 0) {
             if ((e = cudaStreamWaitEvent(stream, la.ev_panel, 0)) != cudaSuccess) return e;
             SyrkJob::Params sp{v, j0, j1, j2, -1, 0};
-            e = gemm_launch<SyrkJob>(ctx, sp, dim3(T2 * (T2 + 1) / 2, batch, 1), stream, j1 - j0);
+            e = syrk(sp, T2 * (T2 + 1) / 2, stream);
             if (e != cudaSuccess) return e;
             if ((e = cudaEventRecord(la.ev_bulk, stream)) != cudaSuccess) return e;
             bulk_pending = true;
