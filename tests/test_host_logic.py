@@ -190,6 +190,16 @@ def test_no_cuda_means_loud_failure():
         Matern32(x, x, np.ones(2), 1.0, 1e-3)
     d = Matern32(x, x, np.ones(2), 2.0, 1e-3, diag_only=True)   # host-only branch, covmat.py:23-29
     np.testing.assert_allclose(d.numpy(), 2.0 * np.ones(30))
+    # the entry points added later fail just as loudly
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.grad_phi()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        LCGP(y=y, x=x, q=2, device_preprocess=True)
+    from lcgp_b200.model import _fullcov_cuda
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _fullcov_cuda(torch.ones(2, 3, dtype=torch.float64), torch.ones(2, 4, dtype=torch.float64),
+                      torch.ones(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64))
+    assert m._dev_prep is False          # constructed on the host pipeline when no CUDA device exists
 
 
 def test_evaluation_metrics():                 # test_diagnostics.py
