@@ -25,7 +25,11 @@ def run(npad, batch, reps=20, check=False):
         Lref = torch.linalg.cholesky(A[0])
         err = (torch.tril(F[0]) - Lref).abs().max().item() / Lref.abs().max().item()
         print(f'   check vs torch.linalg.cholesky: max rel err {err:.2e}  info {info.tolist()}')
-        assert err < 1e-12
+        L00 = torch.tril(F[0][:128, :128])
+        inv_err = (DLb[0, 0] @ L00 - torch.eye(128, dtype=DT, device=dev)).abs().max().item()
+        du_err = (DUb[0, 0] - DLb[0, 0].T).abs().max().item()
+        print(f'   diagonal-block inverse: |DL L - I| {inv_err:.2e}  |DU - DL^T| {du_err:.2e}')
+        assert err < 1e-12 and inv_err < 1e-11 and du_err == 0.0
     ts.sort()
     flops = batch * npad ** 3 / 3
     print(f'np={npad:5d} batch={batch:3d}  median {ts[len(ts)//2]:9.1f} us  min {ts[0]:9.1f} us   {flops / (ts[len(ts)//2] * 1e-6) / 1e12:6.2f} TF/s')
