@@ -40,8 +40,8 @@ def parse():
     ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end fit() wall-time measurement')
     ap.add_argument('--fit-config', default='cfg3_rep',
                     help="configuration of the fit() wall-time measurement; 'workload' = the bench configuration itself "
-                         '(several minutes at config 4 on one GPU); under torchrun the fit runs only when this is given '
-                         'explicitly and is then sharded over the ranks')
+                         '(several minutes at config 4 on one GPU); under torchrun (N > 1) the default is the workload, '
+                         'fitted sharded over the ranks')
     ap.add_argument('--cpu-sample-latents', type=int, default=1)
     ap.add_argument('--emulators', type=int, default=64)      # cfg5_batch only
     ap.add_argument('--threads', type=int, default=4)         # cfg5_batch only: host threads (streams) per GPU (more only contend for the GIL)
@@ -108,22 +108,33 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def dgemm_peak(device, n=6144, reps=4):
-    """cuBLAS DGEMM throughput on this GPU (burst, best of reps): the FP64 tensor-pipe denominator."""
+def dgemm_peak(device, n=8192, reps=4, sustain_s=4.0):
+    """cuBLAS DGEMM throughput on this GPU: the FP64 tensor-pipe denominator.  Returns (burst, sustained) TFLOP/s:
+    best of `reps` single 8192^3 products, and the average over back-to-back products for `sustain_s` seconds."""
     a = torch.randn(n, n, dtype=torch.float64, device=device)
     b = torch.randn(n, n, dtype=torch.float64, device=device)
-    torch.matmul(a, b)
+    c = torch.empty(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b, out=c)
     torch.cuda.synchronize()
     best = 1e30
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        torch.matmul(a, b)
+        torch.matmul(a, b, out=c)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    del a, b
-    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    flop = 2.0 * n ** 3
+    k = max(4, int(sustain_s / (best * 1e-3)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = k * flop / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b, c
+    return flop / (best * 1e-3) / 1e12, sustained
 
 
 def build_model(cfg_name):
@@ -134,12 +145,15 @@ def build_model(cfg_name):
     return model, time.time() - t0, (x, y, mk)
 
 
-def workload_desc(cfg_name, model):
-    return {'workload': f'{cfg_name}: objective+gradient, n={int(model.n)} unique inputs, d={int(model.d)}, '
-                        f'p={int(model.p)}, q={int(model.q)}, submethod={model.submethod}, init_params point',
-            'n': int(model.n), 'd': int(model.d), 'p': int(model.p), 'q': int(model.q),
-            'l2': 'inputs larger than L2 (factor buffers %.1f GB per rank)' % (
-                len(model._local_idx) * (((int(model.n) + 127) // 128 * 128) ** 2) * 8 / 1e9)}
+def workload_desc(cfg_name, n, d, p, q, submethod, world):
+    """`config` of the JSON line -- IDENTICAL in the CUDA arm and the reference arm (arm-specific text lives in the
+    top-level `arm` key), so that the driver's same_config comparison holds."""
+    npad = (n + 127) // 128 * 128
+    return {'workload': f'{cfg_name}: objective+gradient, n={n} unique inputs, d={d}, p={p}, q={q}, '
+                        f'submethod={submethod}, init_params point',
+            'n': n, 'd': d, 'p': p, 'q': q,
+            'l2': 'inputs larger than L2 (%.1f GB of dense n x n factors per evaluation)' % (q * npad ** 2 * 8 / 1e9),
+            'parallelism': f'latents sharded over {world} rank(s)'}
 
 
 def cpu_baseline_sample(x, y, mk, n_latents, q, threads):
@@ -223,15 +237,16 @@ def run_reference(args):
     per_eval = dt * q / args.cpu_sample_latents
     val = 1.0 / per_eval
     sample = (f'{args.cpu_sample_latents} of {q} latents per step at full n (forward + autograd backward), '
-              f'extrapolated x{q // args.cpu_sample_latents}')
+              f'extrapolated x{q // args.cpu_sample_latents}: the reference loop over latents is sequential and every '
+              f'latent costs the same (linearity checked once over all latents: profiles/r2_cpu_full_eval_check.txt)')
     line = {'impl': 'reference', 'metric': 'NLL+grad evals/s', 'value': val, 'unit': 'evals/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_eval * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            # same workload string and keys as the CUDA arm's `config`
-            'config': {'workload': f'{args.config}: objective+gradient, n={int(o.n)} unique inputs, d={int(o.d)}, '
-                                   f'p={int(o.p)}, q={q}, submethod={mk["submethod"]}, init_params point',
-                       'n': int(o.n), 'd': int(o.d), 'p': int(o.p), 'q': q,
-                       'l2': 'n/a (host)', 'parallelism': f'oracle port of the reference CPU path on {threads} host threads'},
+            'config': workload_desc(args.config, int(o.n), int(o.d), int(o.p), q, mk['submethod'], args.gpus),
+            'arm': f'oracle port of the reference CPU path (oracle/lcgp_oracle.py) on {threads} host threads, rank 0 only',
+            # value and ms_per_step are EXTRAPOLATED from the bounded sample each step times
+            'extrapolated': True, 'sampled_latents': args.cpu_sample_latents, 'sample_fraction': args.cpu_sample_latents / q,
+            'sample_ms_per_step': dt * 1e3,
             'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -272,8 +287,10 @@ def run_ours(args):
 
     # ---- warm-up (also through the public API) ----
     for _ in range(max(args.warmup, 3)):
-        device_step()
-    model.loss_and_grad()
+        chk = device_step()
+    if world > 1 and float(chk[-1]) != 0.0:     # last slot of the all-reduced vector: failed latents over all ranks
+        raise SystemExit('bench: Cholesky failure reported by the sharded evaluation')
+    model.loss_and_grad()                       # (single rank: checks `info` itself)
     barrier()
 
     clocks = ClockSampler(local_rank)
@@ -339,32 +356,38 @@ def run_ours(args):
 
     if rank == 0:
         peaks, psrc = measured_peaks()
-        fp64_peak = dgemm_peak(dev)
+        fp64_peak, fp64_sustained = dgemm_peak(dev)
         npad = _cabi.padded(n)
         stage_flops = q_loc * n ** 3 / 3.0             # algorithmic flop of each of the three dense stages on one rank
         tf = lambda ms: stage_flops / (ms * 1e-3) / 1e12
         build_bytes = 8.0 * q_loc * n * (n + 1) / 2     # lower triangle written
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r1_contract_kernel_traffic.json')
-        if os.path.exists(tpath):                       # dram bytes of this launch from the committed ncu capture
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get('q_loc') == q_loc and tj.get('n') == n:
-                traffic = tj['dram_bytes_per_launch']
+        traffic, traffic_source = None, None
+        for tname in ('r2_contract_kernel_traffic.json', 'r1_contract_kernel_traffic.json'):
+            tpath = os.path.join(ROOT, 'profiles', tname)
+            if os.path.exists(tpath):                   # dram bytes of this launch from a COMMITTED ncu capture
+                with open(tpath) as f:                  # (ncu cannot run inside the timed bench): not measured in this run
+                    tj = json.load(f)
+                if tj.get('q_loc') == q_loc and tj.get('n') == n:
+                    traffic, traffic_source = tj['dram_bytes_per_launch'], f'ncu capture profiles/{tname}'
+                    break
         line = {
             'metric': 'NLL+grad evals/s', 'value': args.steps / t_dev, 'unit': 'evals/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_dev / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_desc(args.config, model), parallelism=f'latents sharded over {world} rank(s)'),
+            'config': workload_desc(args.config, n, d, p, q, model.submethod, world),
+            'arm': 'lcgp_b200 CUDA path (liblcgp_b200.so through the C-ABI)',
             'e2e': {'value': args.steps / t_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': eng.h2d_bytes,
-                    'd2h_bytes_per_step': eng.d2h_bytes if world == 1 else (1 + p + q * d + 2 * q) * 8},
+                    'd2h_bytes_per_step': eng.d2h_bytes if world == 1 else (1 + p + q * d + 2 * q + 1) * 8},
             'gpu_launches': launches,
             # dominant kernel: the fused A^-1 / gradient-contraction GEMM, one launch per step (largest
             # single kernel, ~1/3 of the step); timed live with CUDA events recorded around the launch
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_tma_kernel<ContractJob> (A^-1 = U U^T tiles: TMA-staged DMMA GEMM + fused gradient contraction)',
                          'achieved': tf(stages[4]), 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(stages[4]) / fp64_peak,
-                         'peak_source': 'cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
-                         'flops_per_launch': stage_flops, 'kernel_ms': float(stages[4]), 'traffic': traffic},
+                         'peak_source': 'cuBLAS DGEMM 8192^3 burst (best of 4) measured in this run; MEASURED_PEAKS.json has no '
+                                        'FP64 figure and the profiling guide states no FP64 fallback',
+                         'peak_sustained': fp64_sustained, 'frac_of_sustained': tf(stages[4]) / fp64_sustained,
+                         'flops_per_launch': stage_flops, 'kernel_ms': float(stages[4]), 'traffic': traffic,
+                         'traffic_source': traffic_source},
             'stages': {
                 'build_ms': float(stages[0]), 'cholesky_ms': float(stages[1]), 'trtri_ms': float(stages[2]),
                 'solve_ms': float(stages[3]), 'contract_kernel_ms': float(stages[4]), 'tail_ms': float(stages[5]),
@@ -374,7 +397,7 @@ def run_ours(args):
                 'trtri_tflops': tf(stages[2]), 'trtri_frac_of_dgemm': tf(stages[2]) / fp64_peak,
                 'contract_tflops': tf(stages[4]),
                 'whole_eval_tflops': q_loc * float(n) ** 3 / (t_dev / args.steps) / 1e12,
-                'dgemm_peak_tflops': fp64_peak, 'padded_n': npad},
+                'dgemm_peak_tflops': fp64_peak, 'dgemm_sustained_tflops': fp64_sustained, 'padded_n': npad},
             'clocks': clk, 'objective': f_e2e, 'grad_norm': float(np.linalg.norm(g_e2e)), 'ctor_s': t_ctor,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -392,9 +415,11 @@ def run_ours(args):
             line['cpu_baseline'] = None
         line['predict'] = pred
     # ---- fit wall time: every rank takes part when the fit is sharded ----
-    fit_cfg = args.config if args.fit_config == 'workload' else args.fit_config
     fit_explicit = any(a.startswith('--fit-config') for a in sys.argv)
-    if not args.no_fit and (world == 1 or fit_explicit):
+    if world > 1 and not fit_explicit:
+        args.fit_config = 'workload'      # N > 1: the driver-timed fit is the sharded fit of the bench configuration itself
+    fit_cfg = args.config if args.fit_config == 'workload' else args.fit_config
+    if not args.no_fit:
         del model, eng
         torch.cuda.empty_cache()
         cpu_pe = None

@@ -163,6 +163,16 @@ int lcgp_prep_standardize(const double* Y, const double* center, const double* s
 int lcgp_grad_phi(const lcgp_problem* prob, const double* lsigma2_p, void* workspace, size_t workspace_bytes,
                   double* g_phi, void* stream);
 
+/* Sharded evaluation (one rank per GPU, latents k = rank mod world; the reference's q-loop, lcgp.py:605-624, has
+ * no cross-k dependence): rewrites this rank's `out` / `info` of lcgp_nll_grad as the flat vector every rank
+ * all-reduces once per evaluation,
+ *   flat = [objective | d/d lsigma2 (p) | d/d lLmb (q x d) | d/d lLmb0 (q) | d/d lnugGPs (q) | failed latents]
+ * in GLOBAL latent order (1 + p + q d + 2 q + 1 doubles), zero in the rows of latents other ranks own;
+ * loc_of[k] (q int32, device) = local index of latent k on this rank, -1 if not owned.  The last slot counts this
+ * rank's latents whose Cholesky failed, so that after the all-reduce every rank raises together. */
+int lcgp_pack_sharded(const double* out, const int32_t* info, const int32_t* loc_of, int32_t p, int32_t d, int32_t q,
+                      int32_t q_loc, double* flat, void* stream);
+
 /* Copies alpha (CinvMs) and m (mks), each q_loc x n, out of the workspace. */
 int lcgp_get_aux(const lcgp_problem* prob, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,
                  void* stream);

@@ -47,6 +47,7 @@ _SIGS = {
     'lcgp_prep_row_select': (C.c_int, [_dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     'lcgp_prep_standardize': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp]),
     'lcgp_grad_phi': (C.c_int, [C.POINTER(Problem), _dp, _dp, C.c_size_t, _dp, _dp]),
+    'lcgp_pack_sharded': (C.c_int, [_dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     'lcgp_get_aux': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, _dp, _dp, _dp]),
     'lcgp_get_Ainv': (C.c_int, [C.POINTER(Problem), _dp, C.c_size_t, C.c_int32, _dp, _dp]),
     'lcgp_kernel_matrix': (C.c_int, [_dp, C.c_int32, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, _dp]),

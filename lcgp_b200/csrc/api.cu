@@ -276,6 +276,42 @@ finalize_kernel(lcgp_problem P, int nb, int with_grad, const double* __restrict_
         for (int c = tid; c < q * d + 2 * q; c += 256) g_kern[c] *= P.scale;
 }
 
+// Sharded evaluation: this rank's `out` vector (local latent order) -> the flat all-reduce vector
+//   [objective | d/d lsigma2 (p) | d/d lLmb (q x d) | d/d lLmb0 (q) | d/d lnugGPs (q) | number of failed latents]
+// in GLOBAL latent order, zero in the rows of latents other ranks own.  loc_of[k] = local index of latent k, -1 if
+// not owned.  The last slot makes a Cholesky failure collective: after the all-reduce every rank sees it.
+__global__ void pack_sharded_kernel(int p, int d, int q, int q_loc, const int* __restrict__ loc_of,
+                                    const double* __restrict__ out, const int32_t* __restrict__ info,
+                                    double* __restrict__ flat) {
+    const int nflat = 1 + p + q * d + 2 * q;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > nflat) return;
+    if (e == nflat) {
+        int bad = 0;
+        for (int k = 0; k < q_loc; ++k) bad += info[k] != 0;
+        flat[e] = (double)bad;
+        return;
+    }
+    double v = 0.0;
+    if (e < 1 + p) {
+        v = out[e];
+    } else {
+        const double* gk = out + 1 + p;    // local layout: g_ell (q_loc x d), g_s0 (q_loc), g_nug (q_loc)
+        const int c = e - 1 - p;
+        if (c < q * d) {
+            const int l = loc_of[c / d];
+            if (l >= 0) v = gk[(size_t)l * d + c % d];
+        } else if (c < q * d + q) {
+            const int l = loc_of[c - q * d];
+            if (l >= 0) v = gk[(size_t)q_loc * d + l];
+        } else {
+            const int l = loc_of[c - q * d - q];
+            if (l >= 0) v = gk[(size_t)q_loc * d + q_loc + l];
+        }
+    }
+    flat[e] = v;
+}
+
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : 1000 + (int)e; }
 #define LCGP_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_rc(e__); } while (0)
 
@@ -580,6 +616,14 @@ int lcgp_grad_phi(const lcgp_problem* P, const double* lsigma2_p, void* workspac
     // scratch: the GEMV partial-sum area, free once lcgp_nll_grad has finished
     return cuda_rc(grad_phi(view_of(w), P->n, P->p, P->q_loc, P->scale, P->sr, w.mk, lsigma2_p, P->t, P->phi, P->D, w.Z,
                             w.gemv_part, g_phi, (cudaStream_t)stream));
+}
+
+int lcgp_pack_sharded(const double* out, const int32_t* info, const int32_t* loc_of, int32_t p, int32_t d, int32_t q,
+                      int32_t q_loc, double* flat, void* stream) {
+    if (!out || !info || !loc_of || !flat || p <= 0 || d <= 0 || q <= 0 || q_loc <= 0 || q_loc > q) return LCGP_E_ARG;
+    const int nflat = 1 + p + q * d + 2 * q + 1;
+    note_launch(); pack_sharded_kernel<<<(nflat + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, d, q, q_loc, loc_of, out, info, flat);
+    return cuda_rc(cudaGetLastError());
 }
 
 int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes, double* CinvMs, double* mks,

@@ -100,7 +100,12 @@ class CudaEngine:
         self.out_len = int(self.lib.lcgp_out_len(self.p, self.d, self.q_loc))
         q, dd = self.q_loc, self.d
         # pinned host staging: [lLmb | lLmb0 | lnug | lsig_p] and the result vector
-        self.h_par = torch.empty(q * dd + 2 * q + self.p, dtype=DT).pin_memory()
+        # (two pinned buffers, used alternately: evaluate_device does not synchronise the host, so the copy of the
+        # previous call may still be pending when the next call stages its parameters)
+        self._h_pars = [torch.empty(q * dd + 2 * q + self.p, dtype=DT).pin_memory() for _ in range(2)]
+        self._h_par_free = [None, None]      # event recorded after the last asynchronous H2D copy out of each buffer
+        self._h_cur = 0
+        self.h_par = self._h_pars[0]
         self.h_out = torch.empty(self.out_len, dtype=DT).pin_memory()
         self.h_info = torch.zeros(max(q, 1), dtype=torch.int32).pin_memory()
         self.d_par = torch.empty(q * dd + 2 * q + self.p, dtype=DT, device=dev)
@@ -113,14 +118,27 @@ class CudaEngine:
         self._plans = {}
         self._scratch = None
 
-    def _stage(self, lLmb, lLmb0, lnug, lsig_p):
+    def _stage(self, lLmb, lLmb0, lnug, lsig_p, rotate=False):
         q, dd = self.q_loc, self.d
-        h = self.h_par
+        if rotate:      # asynchronous callers: take the other pinned buffer, once its last copy has left it
+            self._h_cur ^= 1
+            ev = self._h_par_free[self._h_cur]
+            if ev is not None:
+                ev.synchronize()
+        h = self._h_pars[self._h_cur] if rotate else self.h_par
         h[:q * dd].copy_(lLmb.reshape(-1))
         h[q * dd:q * dd + q].copy_(lLmb0.reshape(-1))
         h[q * dd + q:q * dd + 2 * q].copy_(lnug.reshape(-1))
         h[q * dd + 2 * q:].copy_(lsig_p.reshape(-1))
         return q * dd, q * dd + q, q * dd + 2 * q
+
+    def _upload_async(self):
+        """d_par <- the pinned buffer _stage(rotate=True) just filled, without a host synchronisation."""
+        self.d_par.copy_(self._h_pars[self._h_cur], non_blocking=True)
+        ev = self._h_par_free[self._h_cur]
+        if ev is None:
+            ev = self._h_par_free[self._h_cur] = torch.cuda.Event()
+        ev.record()
 
     def _events_arg(self, events):
         if events is None:
@@ -174,9 +192,9 @@ class CudaEngine:
     def evaluate_device(self, lLmb, lLmb0, lnug, lsig_p, with_grad=True, events=None):
         """Same, but the result stays on the device (multi-rank path: all-reduce follows on the
         same stream).  No host synchronisation."""
-        o1, o2, o3 = self._stage(lLmb, lLmb0, lnug, lsig_p)
+        o1, o2, o3 = self._stage(lLmb, lLmb0, lnug, lsig_p, rotate=True)
         with torch.cuda.device(self.device):
-            self.d_par.copy_(self.h_par, non_blocking=True)
+            self._upload_async()
             base = self.d_par.data_ptr()
             rc = self.lib.lcgp_nll_grad(self.prob, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
                                         self.ws.data_ptr(), self.ws_bytes, self.d_out.data_ptr(),
@@ -184,6 +202,13 @@ class CudaEngine:
                                         self._events_arg(events), _cabi.stream_ptr())
         _cabi.check(rc, 'lcgp_nll_grad')
         return self.d_out
+
+    def pack_sharded(self, loc_of, q, flat):
+        """d_out / d_info of the last evaluate_device -> the flat all-reduce vector (lcgp_pack_sharded), in place."""
+        with torch.cuda.device(self.device):
+            rc = self.lib.lcgp_pack_sharded(self.d_out.data_ptr(), self.d_info.data_ptr(), loc_of.data_ptr(), self.p,
+                                            self.d, int(q), self.q_loc, flat.data_ptr(), _cabi.stream_ptr())
+        _cabi.check(rc, 'lcgp_pack_sharded')
 
     def _check_info(self, info):
         bad = torch.nonzero(info[:self.q_loc])
@@ -194,10 +219,10 @@ class CudaEngine:
 
     def predict_latents(self, lLmb, lLmb0, lnug, x0s, same):
         """ghat, gvar (q_loc x n0) on the device from the factor left by the last evaluate()."""
-        o1, o2, _ = self._stage(lLmb, lLmb0, lnug, torch.zeros(self.p, dtype=DT))
+        o1, o2, _ = self._stage(lLmb, lLmb0, lnug, torch.zeros(self.p, dtype=DT), rotate=True)
         n0 = int(x0s.shape[0])
         with torch.cuda.device(self.device):
-            self.d_par.copy_(self.h_par, non_blocking=True)
+            self._upload_async()
             x0d = x0s.to(self.device, DT).contiguous()
             need = int(self.lib.lcgp_predict_scratch_bytes(self.n, self.q_loc, n0))
             if self._scratch is None or self._scratch.numel() * 8 < need:
@@ -680,20 +705,29 @@ class LCGP:
         return self._engine
 
     def _evaluate_sharded(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
-        """Multi-rank evaluation: local latents on this rank's engine, then ONE all-reduce of the flat
-        vector [objective | d/d lsigma2 (p) | d/d lLmb (q x d) | d/d lLmb0 (q) | d/d lnugGPs (q)]
-        (each rank fills only its own latents' rows).  Returns the reduced vector on the collective
-        device without synchronising the host."""
+        """Multi-rank evaluation: local latents on this rank's engine, then ONE all-reduce of the flat vector
+        [objective | d/d lsigma2 (p) | d/d lLmb (q x d) | d/d lLmb0 (q) | d/d lnugGPs (q) | failed latents]
+        (each rank fills only its own latents' rows; lcgp_pack_sharded writes it in one launch into a persistent
+        buffer).  Returns the reduced vector on the collective device without synchronising the host.  The last
+        slot makes a Cholesky failure collective: every rank sees the same count and raises together."""
         q, d, p = int(self.q), int(self.d), int(self.p)
         idx = self._local_idx
         eng = self.engine
         ql = idx.numel()
-        nflat = 1 + p + q * d + 2 * q
+        nflat = 1 + p + q * d + 2 * q + 1
         if eng is False:
-            flat = torch.zeros(nflat, dtype=DT, device=self._collective_device())
-        else:
-            dev_eval = getattr(eng, 'evaluate_device', None) or eng.evaluate
-            out = dev_eval(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
+            flat = self._flat_buffer(nflat, self._collective_device())
+            flat.zero_()
+        elif hasattr(eng, 'pack_sharded'):
+            eng.evaluate_device(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
+            flat = self._flat_buffer(nflat, eng.device)
+            if getattr(self, '_loc_of', None) is None:
+                loc = torch.full((q,), -1, dtype=torch.int32)
+                loc[idx] = torch.arange(ql, dtype=torch.int32)
+                self._loc_of = loc.to(eng.device)
+            eng.pack_sharded(self._loc_of, q, flat)
+        else:       # engines without the packing kernel (the CPU stand-in of the gloo tests)
+            out = eng.evaluate(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, need_grad, events)
             flat = torch.zeros(nflat, dtype=DT, device=out.device)
             flat[:1 + p] = out[:1 + p]
             if need_grad:
@@ -705,6 +739,12 @@ class LCGP:
         torch.distributed.all_reduce(flat)
         return flat
 
+    def _flat_buffer(self, nflat, device):
+        buf = getattr(self, '_flat_buf', None)
+        if buf is None or buf.numel() != nflat or buf.device != torch.device(device):
+            buf = self._flat_buf = torch.zeros(nflat, dtype=DT, device=device)
+        return buf
+
     def _evaluate(self, lLmb, lLmb0, lsig_p, lnug, need_grad, events=None):
         """All-latent objective (+ gradient wrt the constrained values) as CPU tensors."""
         q, d, p = int(self.q), int(self.d), int(self.p)
@@ -713,10 +753,10 @@ class LCGP:
         if self._world == 1:
             flat = eng.evaluate(lLmb, lLmb0, lnug, lsig_p, need_grad, events)[:1 + p + q * d + 2 * q]
         else:
-            flat = self._evaluate_sharded(lLmb, lLmb0, lsig_p, lnug, need_grad, events)
-            if flat.is_cuda and eng is not False and hasattr(eng, 'd_info'):
-                eng._check_info(eng.d_info.cpu())
-            flat = flat.cpu()
+            flat = self._evaluate_sharded(lLmb, lLmb0, lsig_p, lnug, need_grad, events).cpu()
+            if float(flat[-1]) != 0.0:     # identical on every rank after the all-reduce: all ranks raise together
+                raise RuntimeError(f'lcgp_b200: Cholesky failed for {int(flat[-1])} latent(s) on some rank '
+                                   f'(A_k = I + d_k R^1/2 C_k R^1/2 has eigenvalues >= 1, so this means NaN/inf inputs)')
         self._factor_key = self._key(lLmb, lLmb0, lsig_p, lnug)
         val = flat[0].clone()
         if not need_grad:

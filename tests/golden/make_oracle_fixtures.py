@@ -22,7 +22,10 @@ from oracle.lcgp_oracle import LCGPOracle  # noqa: E402
 
 def case(name, x, y, x0, **mk):
     o = LCGPOracle(y=y, x=x, **mk)
-    f0, g0 = o.loss_and_grad()
+    # 'full' cases: the Cholesky form of lcgp.py:635-666 (neglpost_chol; equals the literal eigh form to ~1e-15 at
+    # well-conditioned points, tests/test_oracle_selfcheck.py) -- the eigh form itself loses digits through 1/W
+    fn = o.neglpost_chol if mk.get('submethod', 'full') == 'full' else None
+    f0, g0 = o.loss_and_grad(fn)
     rng = np.random.default_rng(11)
     q, d = int(o.q), int(o.d)
     lL = o.lLmb.detach().numpy() * rng.uniform(0.6, 1.6, (q, d))
@@ -30,7 +33,7 @@ def case(name, x, y, x0, **mk):
     ls = o.lsigma2s.detach().numpy() + rng.normal(0, 0.3, o.lsigma2s.numel())
     ln = np.exp(rng.uniform(-12, -5, q))
     o.set_constrained(lL, l0, ls, ln)
-    f1, g1 = o.loss_and_grad()
+    f1, g1 = o.loss_and_grad(fn)
     yp, ypv, ycv = o.predict(torch.as_tensor(x0))
     return {'name': name, 'model': mk, 'init': {'loss': f0, 'grad': g0.tolist()},
             'moved': {'lLmb': lL.tolist(), 'lLmb0': l0.tolist(), 'lsigma2s': ls.tolist(), 'lnugGPs': ln.tolist(),

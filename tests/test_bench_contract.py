@@ -31,7 +31,13 @@ def test_reference_arm_json_contract():
     cb = j['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == j['value'] and 'latents' in cb['sample']
     assert j['e2e'] == {'value': j['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert j['extrapolated'] is True and j['sampled_latents'] == 1 and j['sample_fraction'] == 1 / 8
+    assert abs(j['sample_ms_per_step'] * 8 - j['ms_per_step']) < 1e-6 * j['ms_per_step']
     cfg = j['config']
+    # identical key set and values as the CUDA arm's `config` (bench.workload_desc): no arm-specific text inside
+    sys.path.insert(0, ROOT)
+    import bench
+    assert cfg == bench.workload_desc('cfg5_one', 1024, 6, 64, 8, 'full', 1) and 'arm' in j
     assert cfg['n'] == 1024 and cfg['d'] == 6 and cfg['p'] == 64 and cfg['q'] == 8 and cfg['workload'].startswith('cfg5_one')
 
 
