@@ -197,9 +197,13 @@ int lcgp_build_A(const double* X, const double* sr, int32_t n, int32_t d, const 
 /* In-place batched Cholesky of the lower triangles of `batch` padded np x np matrices
  * (tf.linalg.cholesky, lcgp.py:617/775).  DL/DU receive the inverses of the NB x NB diagonal
  * blocks and their transposes (batch x np/NB x NB x NB each); logdet_part (batch x np/NB, may be
- * NULL) receives sum log L_ii per diagonal block. */
+ * NULL) receives sum log L_ii per diagonal block.
+ * scratch: lcgp_potrf_scratch_bytes(np, batch) bytes of device memory (tile-dependency flags of the persistent
+ * left-looking kernel, ONE launch per call); NULL selects the launch-per-block-column path (as does the
+ * environment variable LCGP_POTRF=panels).  info[b] < 0 reports an internal dependency wait that timed out. */
+size_t lcgp_potrf_scratch_bytes(int32_t np, int32_t batch);
 int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
-                       int32_t* info, void* stream);
+                       int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Blocked triangular inverse: fills the strictly-upper NB-blocks of F with L^{-T}.
  * scratch: lcgp_trtri_scratch_bytes(np, batch). */

@@ -109,10 +109,14 @@ struct Workspace {
     double *F, *DL, *DU, *T, *B, *alpha, *mk, *atil, *gemv_part, *logdet_part, *quad, *tile_part, *V, *Z, *bpart;
     double *ell, *s0, *lnug, *lsig, *out;
     int32_t* info;
+    int* sync;          // flags / ticket counters of the persistent Cholesky kernel, one region per stream group
     size_t total_doubles;
 };
 
 static inline size_t al(size_t x) { return (x + 31) / 32 * 32; }
+// group g (latents [g0, g0 + cnt)) uses the region at sync_off(nb, g, g0) of potrf_pll_sync_ints(nb, cnt) ints
+static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)4 * nb * g0; }
+static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)4 * nb * q; }
 
 static Workspace layout(int n, int d, int p, int q, void* basep) {
     Workspace w;
@@ -147,6 +151,7 @@ static Workspace layout(int n, int d, int p, int q, void* basep) {
     w.lsig = take((size_t)p);
     w.out = take(lcgp_out_len(p, d, q));
     w.info = (int32_t*)take((size_t)(q + 1) / 2 + 1);
+    w.sync = (int*)take((sync_ints(w.nb, q) + 1) / 2);
     w.total_doubles = o;
     return w;
 }
@@ -344,10 +349,16 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     rec(1);
     int G = (flags >> 4) & 15;
     G = G == 0 ? stream_groups(q) : (G > MAX_GROUPS ? MAX_GROUPS : (G > q ? q : G));
+    // The persistent Cholesky kernel keeps every SM it gets until its tickets run out, so concurrent groups mostly run
+    // one after the other and only overlap at their tails; few, small matrices are better off in ONE launch (all
+    // their tiles advance together) unless the caller / environment asked for a group count.
+    const bool pll = potrf_use_pll(w.nb, q);        // decided on this call's whole batch, not per stream group
+    if (pll && ((flags >> 4) & 15) == 0 && !std::getenv("LCGP_STREAMS") && (q < 8 || w.nb <= 16)) G = 1;
     // Look-ahead uses the library's shared high-priority streams: skipped when the caller asked for "everything on
     // my stream" (bits 4-7 == 1: many small emulators driven from several host threads would falsely serialise on
     // them) and for small matrices, where no trailing update is big enough to hide a panel behind.
-    const bool look = lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD) && ((flags >> 4) & 15) != 1 && w.nb > 16;
+    const bool look = !pll && lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD) && ((flags >> 4) & 15) != 1 &&
+                      w.nb > 16;
     auto potrf_group = [&](int g0, int cnt, cudaStream_t s, int g) {
         Lookahead la;
         if (look) {   // run_grouped holds the pool lock
@@ -355,7 +366,8 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
             la.panel = sp.hp[g]; la.ev_panel = sp.evp[g]; la.ev_bulk = sp.evb[g];
         }
         return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
-                             w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s, la);
+                             w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s, la,
+                             pll ? w.sync + sync_off(w.nb, g, g0) : nullptr);
     };
     auto trtri_group = [&](int g0, int cnt, cudaStream_t s, int) {
         return trtri_batched(sub_view(v, g0), w.T + (size_t)g0 * w.tstride, w.tstride, cnt, s);
@@ -702,15 +714,23 @@ int lcgp_build_A(const double* X, const double* sr, int32_t n, int32_t d, const 
     return cuda_rc(launch_build_A(X, sr, n, d, np, kp, F, (size_t)np * np, batch, (cudaStream_t)stream));
 }
 
+size_t lcgp_potrf_scratch_bytes(int32_t np, int32_t batch) {
+    if (np <= 0 || batch <= 0 || np % NB != 0) return 0;
+    return sizeof(int) * potrf_pll_sync_ints(np / NB, batch);
+}
+
 int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
-                       int32_t* info, void* stream) {
+                       int32_t* info, void* scratch, size_t scratch_bytes, void* stream) {
     if (!F || !DL || !DU || !info || np <= 0 || batch <= 0) return LCGP_E_ARG;
     if (np % NB != 0) return LCGP_E_DIM;
+    if (scratch && scratch_bytes < lcgp_potrf_scratch_bytes(np, batch)) return LCGP_E_WORKSPACE;
     FactorView v;
     v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+    if (scratch && potrf_use_pll(v.nb, batch))
+        return cuda_rc(potrf_batched(v, DL, DU, batch, logdet_part, info, panel_width(), st, Lookahead(), (int*)scratch));
     return cuda_rc(run_grouped(st, batch, 1, lookahead_on(), [&](int, int, cudaStream_t s, int g) {
         Lookahead la;
         if (lookahead_on()) {

@@ -2,17 +2,24 @@
 //
 // The block is held as 32 x 32 sub-blocks (pitch 36 doubles: DMMA fragment loads of K-major and N-major operands
 // are bank-conflict free for any pitch = 4 mod 16).  Blocked right-looking factorisation over 4 sub-block columns:
-//   P1  warp 0 factors the 32 x 32 diagonal sub-block in registers (lane = row): per column ONE shuffle round
-//       (the unscaled column), a reciprocal and a fused update -- the division-free "LDL^T in flight" form keeps
-//       the square root off the dependent chain (~100 cycles per column instead of ~900 in the column-by-column
-//       kernel this replaces, where every column was a CTA-wide hand-off)
-//   P2  forward substitutions against that sub-block, one LANE per right-hand side: warp 0 solves for the identity
-//       (-> the inverse of the sub-block), warps 1.. solve for the rows of the panel below (X = A L^-T)
-//   P3  trailing update S -= X X^T on the FP64 tensor pipe (DMMA m8n8k4 from shared memory)
+//   panel  the tall panel [diagonal sub-block ; rows below ; I_32] is eliminated column by column by all 256 threads
+//          (panel32 below): the rows below come out as X = A L_ss^-T and the identity rows as the inverse of the
+//          diagonal sub-block, so there is no separate triangular solve / inverse pass
+//   P3     trailing update S -= X X^T on the FP64 tensor pipe (DMMA m8n8k4 from shared memory)
 // and then the inverse of the whole block by two levels of block merges W21 = -W22 (L21 W11), again on DMMA.
-// Everything is CTA-local (__syncthreads between phases); ~12 us per block instead of 58.
+// Everything is CTA-local (__syncthreads between phases).  Measured on B200 (tools/ubench/diag_phases.cu, cycles at
+// 1.965 GHz): load 7 k, panels 4 x 10.5 k, P3 9 k, inverse merges 10 k, stores (L, DL, DU) 16 k: ~43 us per block, of
+// which the stores of L and DU can follow the hand-off of DL (was 58 us for the register-resident column-by-column
+// kernel).  What was tried on the way: one warp per 32 x 32 sub-block with 64-bit shuffles (12.2 k cycles per
+// sub-block: a 64-bit SHFL costs ~13 issue cycles) or with a shared-memory column broadcast (6.7 k) plus per-lane
+// forward substitutions (2.7 k): one warp can issue a DFMA only every ~6 cycles, so the rank-1 FMAs must be spread
+// over all warps; what remains is the dependent chain LDS -> reciprocal (47) -> multiply -> FMA -> STS -> barrier.
 #pragma once
 #include "common.cuh"
+
+#ifndef C128_STAMP              // profiling hook of tools/ubench/diag_phases.cu: records a time stamp per phase
+#define C128_STAMP(id)
+#endif
 
 namespace lcgp {
 namespace c128 {
@@ -28,46 +35,122 @@ constexpr int OFF_W = NBLK * BLK;
 constexpr int OFF_PIV = 2 * NBLK * BLK;
 constexpr int OFF_INVD = OFF_PIV + NB;
 constexpr int OFF_RED = OFF_INVD + NB;
-constexpr int SMEM_DOUBLES = OFF_RED + 16;
-constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;   // 186,496 B
+constexpr int OFF_COL = OFF_RED + 16;           // column broadcast buffers of panel32 (2 x 160)
+constexpr int SMEM_DOUBLES = OFF_COL + 2 * 160;
+constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;   // 189,056 B
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// ---- P1: in-warp Cholesky of a 32 x 32 block.  Lane i holds row i (a[j], j <= i valid; 0 above the diagonal).
-// On return a[j] (j <= i) = L[i][j]; pivs[c] / invd[c] (shared) = pivot d_c and 1 / L_cc.
-__device__ __forceinline__ void potrf32_warp(double (&a)[SB], int lane, double* __restrict__ pivs,
-                                             double* __restrict__ invd) {
+// ---- Panel factorisation of sub-block column s by the whole CTA (256 threads) ------------------------------------
+// The tall panel  [ S(s,s) ; S(s+1..3, s) ; I_32 ]  (160 - 32 s rows x 32 columns) is eliminated column by column
+// (right-looking, unscaled "LDL^T in flight" form: a_ij -= u_i u_j / d, the square roots are applied at the end).
+// Rows below the diagonal sub-block come out as X = A L_ss^-T, the identity rows as L_ss^-T = W_ss^T -- so the
+// panel solve and the inverse of the diagonal sub-block cost no separate pass.
+// Thread (rg = tid / 4, tx = tid % 4) owns rows rho = rg + 64 m (m < 3) and columns j = tx + 4 n (n < 8): the columns
+// still active at step c are spread evenly over the threads (one warp can issue a DFMA only every ~6 cycles, so the
+// rank-1 updates must be spread over all warps).  Column c is published through shared memory (double buffered),
+// ONE CTA barrier per column; the owners of column c + 1 update and publish it before their other updates.
+// Dependent chain per column:  LDS -> reciprocal -> multiply -> FMA -> STS -> barrier (~130 cycles); measured ~300 per
+// column including the rank-1 FMAs (a warp issues one DFMA per ~6 cycles; 21 per thread and column at most).
+constexpr int CBP = 160;                // doubles per column buffer
+__device__ __forceinline__ void bar_cta() { __syncthreads(); }
+
+// The 32 column steps for a thread that owns mr <= MR rows (rho[0..mr)) x 8 columns (tx + 4 n).  ONE instantiation for
+// the whole CTA: per-warp instantiations by row count (fewer wasted FMAs) were measured and gave wrong results --
+// barriers reached from different code copies did not order the column buffers -- for a 15 % gain at best.
+template <int MR>
+__device__ __forceinline__ void panel32_cols(double (&a)[3][8], const int (&rho)[3], int tx, double* __restrict__ colbuf,
+                                             double* __restrict__ pivs, int mr) {
 #pragma unroll
     for (int c = 0; c < SB; ++c) {
-        const double d = __shfl_sync(0xffffffffu, a[c], c);
-        const double rd = fast_rcp(d);
-        double t = a[c] * rd;                       // u_i / d  (u = unscaled column c)
-        t = (lane >= c) ? t : 0.0;                  // rows above the column stay exactly zero
+        const double* cb = colbuf + (c & 1) * CBP;
+        double* nb_ = colbuf + ((c + 1) & 1) * CBP;
+        const int n0 = c >> 2;                      // column groups n < n0 are finished; n == n0 is active iff tx > (c & 3)
+        const int n1 = (c + 1) >> 2;                // group of column c + 1
+        const double d = cb[c];
+        double t[MR], u[8];
 #pragma unroll
-        for (int j = c + 1; j < SB; ++j) {
-            const double uj = __shfl_sync(0xffffffffu, a[c], j);
-            a[j] = fma(-t, uj, a[j]);               // a_ij -= u_i u_j / d   (meaningful for i >= j)
+        for (int m = 0; m < MR; ++m) t[m] = (m < mr) ? cb[rho[m]] : 0.0;
+#pragma unroll
+        for (int n = n0; n < 8; ++n) u[n] = cb[tx + 4 * n];      // all reads of this buffer happen before the barrier
+        const double rd = fast_rcp(d);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) t[m] *= rd;
+        if (threadIdx.x == 0) pivs[c] = d;
+        if (c + 1 < SB) {                           // column c + 1 first; its owners publish it at once
+            if ((n1 > n0) || (tx > (c & 3))) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) a[m][n1] = fma(-t[m], u[n1], a[m][n1]);
+            }
+            if (tx == ((c + 1) & 3)) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m)
+                    if (m < mr) nb_[rho[m]] = a[m][n1];
+            }
         }
-        const double rs = rsqrt(d);                 // off the dependent chain: nothing below waits for it
-        a[c] = (lane == c) ? d * rs : a[c] * rs;
-        if (lane == c) { pivs[c] = d; invd[c] = rs; }
+        bar_cta();
+        // the rest of the rank-1 update (registers only): overlaps the next column's loads and reciprocal
+#pragma unroll
+        for (int n = n0; n < 8; ++n) {
+            if (n == n1 && c + 1 < SB) continue;
+            if ((n > n0) || (tx > (c & 3))) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) a[m][n] = fma(-t[m], u[n], a[m][n]);
+            }
+        }
     }
 }
 
-// ---- P2: forward substitution  L x = r  against the transposed block Lt[k * LTP + i] = L[i][k]; one right-hand
-// side per lane, in registers.  invd[k] = 1 / L_kk.
-__device__ __forceinline__ void fwdsub32(double (&r)[SB], const double* __restrict__ Lt,
-                                         const double* __restrict__ invd) {
+__device__ __forceinline__ void panel32(double* __restrict__ sm, int s) {
+    double* S = sm + OFF_S;
+    double* W = sm + OFF_W;
+    double* pivs = sm + OFF_PIV + s * SB;
+    double* invd = sm + OFF_INVD + s * SB;
+    double* colbuf = sm + OFF_COL;
+    const int tid = threadIdx.x, rg = tid >> 2, tx = tid & 3;
+    const int nbelow = (3 - s) * SB;                // rows below the diagonal sub-block
+    const int NR = 2 * SB + nbelow;                 // + diagonal sub-block + identity rows: 160, 128, 96, 64
+    const int mr = (NR + 63 - rg) >> 6;             // rows rho = rg + 64 m < NR owned by this thread: warp-uniform, 1..3
+    double a[3][8];
+    double* rowp[3];                                // shared-memory row of a data row (null: identity row / unused)
+    int rho[3];
 #pragma unroll
-    for (int k = 0; k < SB; ++k) {
-        const double w = r[k] * invd[k];
-        r[k] = w;
-        if (((k + 1) & 1) && k + 1 < SB) r[k + 1] = fma(-Lt[k * LTP + k + 1], w, r[k + 1]);   // odd first row: single
+    for (int m = 0; m < 3; ++m) {
+        rho[m] = rg + 64 * m;
+        const bool valid = m < mr;
+        rowp[m] = nullptr;
+        if (valid && rho[m] < SB) rowp[m] = S + tri(s, s) * BLK + rho[m] * BP;
+        else if (valid && rho[m] < SB + nbelow) rowp[m] = S + tri(s + 1 + ((rho[m] - SB) >> 5), s) * BLK + ((rho[m] - SB) & 31) * BP;
 #pragma unroll
-        for (int i = (k + 2) & ~1; i < SB; i += 2) {       // aligned pairs: one 16-byte broadcast load each
-            const double2 l2 = *reinterpret_cast<const double2*>(Lt + k * LTP + i);
-            r[i] = fma(-l2.x, w, r[i]);
-            r[i + 1] = fma(-l2.y, w, r[i + 1]);
+        for (int n = 0; n < 8; ++n) {
+            const int j = tx + 4 * n;
+            a[m][n] = rowp[m] ? rowp[m][j] : ((valid && rho[m] - SB - nbelow == j) ? 1.0 : 0.0);
+        }
+    }
+    if (tx == 0) {                                  // publish column 0
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+            if (m < mr) colbuf[rho[m]] = a[m][0];
+    }
+    bar_cta();
+    panel32_cols<3>(a, rho, tx, colbuf, pivs, mr);
+    // 1 / L_cc = rsqrt(d_c), once per column
+    if (tid < SB) invd[tid] = rsqrt(pivs[tid]);
+    bar_cta();
+    double* Wd = W + tri(s, s) * BLK;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        if (m >= mr) continue;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int j = tx + 4 * n;
+            const double v = a[m][n] * invd[j];
+            if (rho[m] < SB) rowp[m][j] = (j <= rho[m]) ? v : 0.0;              // L_ss (zeros above the diagonal)
+            else if (rowp[m]) rowp[m][j] = v;                                    // X = A L_ss^-T
+            else {                                                               // identity row i: W_ss[j][i]
+                const int i = rho[m] - SB - nbelow;
+                Wd[j * BP + i] = (j >= i) ? v : 0.0;
+            }
         }
     }
 }
@@ -126,46 +209,15 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
     const int g = lane >> 2, t = lane & 3;
     double* S = sm + OFF_S;
     double* W = sm + OFF_W;
-    double* pivs = sm + OFF_PIV;
-    double* invd = sm + OFF_INVD;
-    double* Lt = W + tri(3, 0) * BLK;       // scratch until the level-2 merge writes W(3,0)
 
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
-        double* Sd = S + tri(s, s) * BLK;
-        // ---- P1: diagonal sub-block (warp 0)
-        if (warp == 0) {
-            double a[SB];
-#pragma unroll
-            for (int j = 0; j < SB; ++j) a[j] = (j <= lane) ? Sd[lane * BP + j] : 0.0;
-            potrf32_warp(a, lane, pivs + s * SB, invd + s * SB);
-#pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                Sd[lane * BP + j] = (j <= lane) ? a[j] : 0.0;      // L_ss, row-major
-                Lt[j * LTP + lane] = a[j];                          // transposed copy (entries i >= k are read)
-            }
-        }
+        C128_STAMP(4 * s + 0);
+        // ---- P1 + P2: panel factorisation (diagonal sub-block, rows below, inverse of the sub-block)
+        panel32(sm, s);
         __syncthreads();
-        // ---- P2: substitutions, one right-hand side per lane
-        const int mrows = (3 - s) * SB;                             // panel rows below
-        if (warp == 0) {                                            // identity -> W(s,s) = inv(L_ss), column `lane`
-            double r[SB];
-#pragma unroll
-            for (int i = 0; i < SB; ++i) r[i] = (i == lane) ? 1.0 : 0.0;
-            fwdsub32(r, Lt, invd + s * SB);
-            double* Wd = W + tri(s, s) * BLK;
-#pragma unroll
-            for (int i = 0; i < SB; ++i) Wd[i * BP + lane] = (i >= lane) ? r[i] : 0.0;
-        } else if ((warp - 1) * SB < mrows) {                        // warp w: panel sub-block (s + w, s), row `lane`
-            double* Sp = S + tri(s + warp, s) * BLK;
-            double r[SB];
-#pragma unroll
-            for (int i = 0; i < SB; ++i) r[i] = Sp[lane * BP + i];
-            fwdsub32(r, Lt, invd + s * SB);
-#pragma unroll
-            for (int i = 0; i < SB; ++i) Sp[lane * BP + i] = r[i];
-        }
-        __syncthreads();
+        C128_STAMP(4 * s + 1);
+        C128_STAMP(4 * s + 2);
         // ---- P3: trailing update S(bi,bj) -= X_bi X_bj^T, units of 16 rows x 32 columns
         {
             const int nt = 3 - s;                                   // trailing sub-block rows
@@ -184,8 +236,10 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
         __syncthreads();
     }
     // ---- L is complete: let the caller save it before the diagonal S blocks become scratch
+    C128_STAMP(16);
     write_L();
     __syncthreads();
+    C128_STAMP(17);
     // ---- inverse, level 1: W(1,0) = -W(1,1) (L(1,0) W(0,0)),  W(3,2) = -W(3,3) (L(3,2) W(2,2))
     {
         double acc[2][4][2];
@@ -203,6 +257,7 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
             store_unit<false>(W + tri(2 * m + 1, 2 * m) * BLK + half * 16 * BP, acc, -1.0, g, t);
         }
         __syncthreads();
+        C128_STAMP(18);
         // ---- level 2: T2 = L[2:4][0:2] W[0:2][0:2] (into the diagonal S blocks), W[2:4][0:2] = -W[2:4][2:4] T2
         // unit = warp: output block (a, b) = (2 + (warp >> 2), (warp >> 1) & 1), half = warp & 1;  T2(a,b) lives in S(2(a-2)+b, same)
         const int a2 = 2 + (warp >> 2), b2 = (warp >> 1) & 1, half = warp & 1;
@@ -221,59 +276,117 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
         zero_acc(acc);
         mma_unit<true>(W + tri(a2, 2) * BLK + half * 16 * BP, S + tri(b2, b2) * BLK, acc, g, t);              // W(a,2) T2(2,b)
         if (a2 == 3) mma_unit<true>(W + tri(3, 3) * BLK + half * 16 * BP, S + tri(2 + b2, 2 + b2) * BLK, acc, g, t);  // W(3,3) T2(3,b)
-        // (Lt scratch lived in W(3,0): last read in step s = 3, two barriers ago)
         store_unit<false>(W + tri(a2, b2) * BLK + half * 16 * BP, acc, -1.0, g, t);
         __syncthreads();
+        C128_STAMP(19);
     }
 }
 
 // ---- global <-> shared ----------------------------------------------------------------------------------
-// Loads the lower triangle of the 128 x 128 block at blk (row-major, ld) into the S sub-blocks (zeros above the diagonal
-// of the diagonal sub-blocks).  L2 loads (the block may have been written by another SM of the same kernel).
-__device__ __forceinline__ void load_block(double* __restrict__ sm, const double* __restrict__ blk, size_t ld) {
+// Loads rows [r0, r0 + NR) of the lower triangle of the 128 x 128 block at blk (row-major, ld) into the S sub-blocks
+// (zeros above the diagonal of the diagonal sub-blocks).  L2 loads (the block may have been written by another SM of
+// the same kernel); 16 loads per thread are in flight before the first is consumed.  NR = 128 or 64.
+template <int NR>
+__device__ __forceinline__ void load_rows(double* __restrict__ sm, const double* __restrict__ blk, size_t ld, int r0) {
     double* S = sm + OFF_S;
-    for (int idx = threadIdx.x; idx < NB * (NB / 2); idx += blockDim.x) {
-        const int r = idx >> 6, c = (idx & 63) * 2;
-        if (c > r) continue;
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(blk + (size_t)r * ld + c));
-        double* q = S + tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31);
-        q[0] = v.x;
-        q[1] = (c + 1 <= r) ? v.y : 0.0;
+    constexpr int PAIRS = NR * (NB / 2);
+    static_assert(PAIRS % (256 * 16) == 0, "load_rows assumes 256 threads");
+#pragma unroll 1
+    for (int base = 0; base < PAIRS; base += 256 * 16) {
+        double2 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = base + u * 256 + threadIdx.x;
+            const int r = r0 + (idx >> 6), c = (idx & 63) * 2;
+            v[u] = (c <= r) ? __ldcg(reinterpret_cast<const double2*>(blk + (size_t)r * ld + c)) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = base + u * 256 + threadIdx.x;
+            const int r = r0 + (idx >> 6), c = (idx & 63) * 2;
+            if ((c >> 5) <= (r >> 5)) {             // sub-block on or below the diagonal (zeros above the diagonal inside it)
+                double* q = S + tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31);
+                *reinterpret_cast<double2*>(q) = make_double2(v[u].x, (c + 1 <= r) ? v[u].y : 0.0);
+            }
+        }
     }
-    // zero the rest of the upper triangle of the diagonal sub-blocks (pairs skipped above)
-    for (int idx = threadIdx.x; idx < 4 * SB * (SB / 2); idx += blockDim.x) {
-        const int s = idx >> 9, r = (idx >> 4) & 31, c = (idx & 15) * 2;
-        if (c > r) {
-            double* q = S + tri(s, s) * BLK + r * BP + c;
-            q[0] = 0.0;
-            q[1] = 0.0;
+}
+__device__ __forceinline__ void load_block(double* __restrict__ sm, const double* __restrict__ blk, size_t ld) {
+    load_rows<NB>(sm, blk, ld, 0);
+}
+
+// One accumulator pair (row r, columns c, c + 1 of the block; c even) -> S sub-blocks, as load_rows would place it
+__device__ __forceinline__ void put_pair(double* __restrict__ sm, int r, int c, double v0, double v1) {
+    if ((c >> 5) <= (r >> 5)) {
+        double* q = sm + OFF_S + tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31);
+        *reinterpret_cast<double2*>(q) = make_double2((c <= r) ? v0 : 0.0, (c + 1 <= r) ? v1 : 0.0);
+    }
+}
+
+// L (lower triangle incl. diagonal) -> global block; DIAG selects the diagonal sub-blocks (which the inverse phase
+// overwrites) or the sub-blocks below them (which it leaves alone)
+template <bool DIAG>
+__device__ __forceinline__ void store_L_part(const double* __restrict__ sm, double* __restrict__ blk, size_t ld) {
+    const double* S = sm + OFF_S;
+    constexpr int PAIRS = NB * (NB / 2);
+#pragma unroll 1
+    for (int base = 0; base < PAIRS; base += 256 * 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 256 + threadIdx.x;
+            const int r = idx >> 6, c = (idx & 63) * 2;
+            if (c <= r && ((r >> 5) == (c >> 5)) == DIAG) {
+                const double2 v = *reinterpret_cast<const double2*>(S + tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31));
+                if (c + 1 <= r) *reinterpret_cast<double2*>(blk + (size_t)r * ld + c) = v;
+                else blk[(size_t)r * ld + c] = v.x;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void store_L(const double* __restrict__ sm, double* __restrict__ blk, size_t ld) {
+    store_L_part<true>(sm, blk, ld);
+    store_L_part<false>(sm, blk, ld);
+}
+
+// DL = W (dense, zeros above the diagonal), NB x NB row-major
+__device__ __forceinline__ void store_DL(const double* __restrict__ sm, double* __restrict__ dl) {
+    const double* W = sm + OFF_W;
+    constexpr int PAIRS = NB * (NB / 2);
+#pragma unroll 1
+    for (int base = 0; base < PAIRS; base += 256 * 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 256 + threadIdx.x;
+            const int r = idx >> 6, c = (idx & 63) * 2;
+            double2 v = make_double2(0.0, 0.0);
+            if (c <= r) {
+                v = *reinterpret_cast<const double2*>(W + tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31));
+                if (c + 1 > r) v.y = 0.0;
+            }
+            *reinterpret_cast<double2*>(dl + (size_t)r * NB + c) = v;
         }
     }
 }
 
-// L (lower triangle incl. diagonal) -> global block
-__device__ __forceinline__ void store_L(const double* __restrict__ sm, double* __restrict__ blk, size_t ld) {
-    const double* S = sm + OFF_S;
-    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        if (c <= r) blk[(size_t)r * ld + c] = S[tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31)];
+// DU = W^T.  Transposed read: a warp covers 4 rows x 8 columns of DU per step (64-byte global segments, conflict-free LDS)
+__device__ __forceinline__ void store_DU(const double* __restrict__ sm, double* __restrict__ du) {
+    const double* W = sm + OFF_W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cl = lane >> 2, rl = lane & 3;
+#pragma unroll 1
+    for (int p0 = warp; p0 < (NB / 4) * (NB / 8); p0 += 8 * 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int patch = p0 + u * 8;
+            const int r = (patch >> 4) * 4 + rl, c = (patch & 15) * 8 + cl;
+            du[r * NB + c] = (c >= r) ? W[tri(c >> 5, r >> 5) * BLK + (c & 31) * BP + (r & 31)] : 0.0;
+        }
     }
 }
 
-// DL = W (dense, zeros above the diagonal), DU = W^T; both NB x NB row-major
 __device__ __forceinline__ void store_inverse(const double* __restrict__ sm, double* __restrict__ dl, double* __restrict__ du) {
-    const double* W = sm + OFF_W;
-    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        dl[idx] = (c <= r) ? W[tri(r >> 5, c >> 5) * BLK + (r & 31) * BP + (c & 31)] : 0.0;
-    }
-    // transposed read: a warp covers 4 rows x 8 columns of DU per step (64-byte global segments, conflict-free LDS)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int cl = lane >> 2, rl = lane & 3;
-    for (int patch = warp; patch < (NB / 4) * (NB / 8); patch += nw) {
-        const int r = (patch >> 4) * 4 + rl, c = (patch & 15) * 8 + cl;
-        du[r * NB + c] = (c >= r) ? W[tri(c >> 5, r >> 5) * BLK + (c & 31) * BP + (r & 31)] : 0.0;
-    }
+    store_DL(sm, dl);
+    store_DU(sm, du);
 }
 
 }  // namespace c128

@@ -16,8 +16,17 @@ struct Lookahead {
     cudaStream_t panel = nullptr;
     cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
 };
+// sync != nullptr (potrf_pll_sync_ints(nb, batch) ints of device scratch) selects the persistent left-looking kernel
+// of potrf_pll.cu (one launch per call) unless LCGP_POTRF=panels; otherwise the launch-per-block-column path below.
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, int panel_width, cudaStream_t stream, const Lookahead& la = Lookahead());
+                          int* info, int panel_width, cudaStream_t stream, const Lookahead& la = Lookahead(),
+                          int* sync = nullptr);
+bool potrf_use_pll();                     // the persistent kernel is enabled at all (LCGP_POTRF != panels, TMA engine)
+bool potrf_use_pll(int nb, int batch);    // ... and selected for this batch of matrices
+// potrf_pll.cu
+size_t potrf_pll_sync_ints(int nb, int batch);
+cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part, int* info,
+                      int* sync, cudaStream_t stream);
 size_t trtri_scratch_blocks(int nb);
 void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[]);
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);

@@ -6,6 +6,7 @@
 //   TRTRI: bottom-up binary merges of already-inverted diagonal ranges, two DMMA GEMMs per level.
 #include <atomic>
 
+#include "chol128.cuh"
 #include "gemm_dmma.cuh"
 #include "lcgp_internal.h"
 
@@ -37,6 +38,33 @@ constexpr int LCGP_MAX_PANELS = 4096;
 // as many 64 x 128 tiles: they sit on the serial panel chain and leave SMs idle anyway, so halving the work per CTA
 // halves their latency.  0 = never.
 static int half_tile_limit() { static const int v = env_clamped("LCGP_HALF_TILES", 74, 0, 1 << 20); return v; }
+
+// LCGP_POTRF = pll (one persistent kernel per factorisation, potrf_pll.cu) | panels (launch chain below) | auto
+// (default): the persistent kernel except for large batches of large matrices (>= 16 matrices of >= 32 block columns),
+// where the launch chain with its K = 1024 trailing updates is still ~1.5 % faster (config 4 on one GPU: 169.0 vs
+// 171.5 ms; profiles/r2_potrf_pll_vs_panels.txt) -- everywhere else the persistent kernel wins by 10-45 %.
+static int potrf_mode() {   // 0 = auto, 1 = pll, 2 = panels
+    static const int v = [] {
+        const char* e = std::getenv("LCGP_POTRF");
+        if (e && std::strcmp(e, "panels") == 0) return 2;
+        if (e && std::strcmp(e, "pll") == 0) return 1;
+        return 0;
+    }();
+    return v;
+}
+bool potrf_use_pll() { return potrf_mode() != 2 && gemm_use_tma(); }
+bool potrf_use_pll(int nb, int batch) {
+    if (!potrf_use_pll()) return false;
+    return potrf_mode() == 1 || !(batch >= 16 && nb >= 32);
+}
+// LCGP_DIAG = v2 (default: blocked shared-memory kernel, chol128.cuh) | v1 (register-resident column-by-column kernel)
+static bool diag_use_v2() {
+    static const bool v = [] {
+        const char* e = std::getenv("LCGP_DIAG");
+        return !(e && std::strcmp(e, "v1") == 0);
+    }();
+    return v;
+}
 
 int gemm_tma_min_kblocks() {
     static const int v = [] {
@@ -277,6 +305,28 @@ potrf_diag_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet
     if (tid == 0 && logdet_part) logdet_part[(size_t)bz * v.nb + jb] = lg;
 }
 
+// Diagonal-block kernel, second generation: one CTA per matrix, block resident in shared memory as 32 x 32 sub-blocks;
+// in-warp factorisation of the sub-blocks, substitutions with one lane per right-hand side, DMMA for the trailing
+// updates and for the inverse (chol128.cuh).
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+potrf_diag2_kernel(FactorView v, double* DLw, double* DUw, int jb, double* logdet_part, int* info) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, bz = blockIdx.x;
+    double* blk = v.F + (size_t)bz * v.fstride + (size_t)jb * NB * v.np + (size_t)jb * NB;
+    c128::load_block(sm, blk, v.np);
+    __syncthreads();
+    c128::factor_invert(sm, [&] { c128::store_L(sm, blk, v.np); });
+    c128::store_inverse(sm, DLw + (size_t)bz * v.dstride + (size_t)jb * NB * NB, DUw + (size_t)bz * v.dstride + (size_t)jb * NB * NB);
+    const double* pivs = sm + c128::OFF_PIV;
+    if (tid == 0) {
+        for (int c = 0; c < NB; ++c)
+            if (!(pivs[c] > 0.0)) { atomicCAS(&info[bz], 0, jb * NB + c + 1); break; }
+    }
+    double lg = (tid < NB) ? 0.5 * log(pivs[tid]) : 0.0;
+    lg = block_sum(lg, sm + c128::OFF_RED);
+    if (tid == 0 && logdet_part) logdet_part[(size_t)bz * v.nb + jb] = lg;
+}
+
 static cudaError_t diag_configure() {
     static std::atomic<bool> done[MAX_DEVICES];
     int dev = 0;
@@ -284,6 +334,8 @@ static cudaError_t diag_configure() {
     if (dev < 0 || dev >= MAX_DEVICES) dev = 0;
     if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c128::SMEM_BYTES);
     if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
     return e;
 }
@@ -302,7 +354,8 @@ static cudaError_t diag_configure() {
 //     bulk :            wait factor k  | update_k(cols right of panel k+1) | ...
 // Events are re-recorded every panel (a wait refers to the record that precedes it in host order).
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, int pw, cudaStream_t stream, const Lookahead& la) {
+                          int* info, int pw, cudaStream_t stream, const Lookahead& la, int* sync) {
+    if (sync && potrf_use_pll()) return potrf_pll(v, DLw, DUw, batch, logdet_part, info, sync, stream);   // callers apply the size rule
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
     if (pw < 1) pw = batch >= 8 ? 16 : 8;   // auto: wide panels pay once the batch alone fills the SMs
@@ -346,7 +399,9 @@ cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int bat
                     e = gemm_launch<SyrkJob>(ctx, cp, dim3(v.nb - j, batch, 1), ps, j - j0);
                 if (e != cudaSuccess) return e;
             }
-            note_launch(); potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, ps>>>(v, DLw, DUw, j, logdet_part, info);
+            note_launch();
+            if (diag_use_v2()) potrf_diag2_kernel<<<batch, DIAG_THREADS, c128::SMEM_BYTES, ps>>>(v, DLw, DUw, j, logdet_part, info);
+            else potrf_diag_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, ps>>>(v, DLw, DUw, j, logdet_part, info);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             const int T = v.nb - j - 1;

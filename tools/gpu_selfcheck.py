@@ -69,7 +69,8 @@ def stage_check(n=300, d=3, q=2, seed=0):
     DU = torch.zeros((q, nb, 128, 128), dtype=DT, device=dev)
     ldp = torch.zeros((q, nb), dtype=DT, device=dev)
     info = torch.zeros(q, dtype=torch.int32, device=dev)
-    rc = L.lcgp_potrf_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), ldp.data_ptr(), info.data_ptr(), st)
+    sb = int(L.lcgp_potrf_scratch_bytes(npad, q)); pscr = torch.zeros(sb // 4, dtype=torch.int32, device=F.device)
+    rc = L.lcgp_potrf_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), ldp.data_ptr(), info.data_ptr(), pscr.data_ptr(), sb, st)
     torch.cuda.synchronize()
     L_ref = torch.linalg.cholesky(A_ref)
     Fc = F.cpu()

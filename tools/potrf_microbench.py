@@ -12,13 +12,17 @@ def run(npad, batch, reps=20, check=False):
     DLb = torch.zeros((batch, nb, 128, 128), dtype=DT, device=dev); DUb = torch.zeros_like(DLb)
     info = torch.zeros(batch, dtype=torch.int32, device=dev)
     st = _cabi.stream_ptr()
+    sb = int(L.lcgp_potrf_scratch_bytes(npad, batch))
+    scr = torch.zeros(max(sb // 4, 1), dtype=torch.int32, device=dev)
+    legacy = os.environ.get('LCGP_POTRF') == 'panels'
     ts = []
     for r in range(reps):
         F = A.clone()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        L.lcgp_potrf_batched(F.data_ptr(), npad, batch, DLb.data_ptr(), DUb.data_ptr(), None, info.data_ptr(), st)
+        L.lcgp_potrf_batched(F.data_ptr(), npad, batch, DLb.data_ptr(), DUb.data_ptr(), None, info.data_ptr(),
+                             None if legacy else scr.data_ptr(), 0 if legacy else sb, st)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     if check and not os.environ.get('LCGP_DIAG_MODE'):
