@@ -48,7 +48,12 @@ typedef struct lcgp_problem {
     int32_t p;       /* output dimension */
     int32_t q_loc;   /* latent components handled by this rank */
     int32_t include_host_terms; /* 1: add the O(p) data-fit / noise / -p/2 sum log r terms (one rank only) */
-    int32_t reserved;
+    int32_t n_emu;      /* 0 or 1: one emulator.  E > 1: the call evaluates E INDEPENDENT emulators of identical
+                           (n, d, p) and q_loc / E latents each (BASELINE config 5: batched fits / restarts); every
+                           array below then carries a leading emulator dimension (X: E x n x d, sr: E x n, YR: E x p x n,
+                           w, t: E x p, phi: E x p x q_per, D: E x q_per), the parameters are lLmb (q_loc x d), lLmb0,
+                           lnugGPs (q_loc) and lsigma2_p (E x p), and `out` holds E consecutive blocks of
+                           lcgp_out_len(p, d, q_loc / E) doubles, one objective and gradient per emulator */
     double scale;       /* objective multiplier: 1/n (rep) or 1 (full) */
     double sum_log_r;
     const double* X;    /* n x d */
@@ -58,6 +63,7 @@ typedef struct lcgp_problem {
     const double* t;    /* p */
     const double* phi;  /* p x q_loc  (this rank's columns of the basis) */
     const double* D;    /* q_loc      (diag_D of this rank's latents) */
+    const double* emu_consts; /* n_emu > 1: E x 2 device array (scale, sum_log_r) per emulator; otherwise NULL */
 } lcgp_problem;
 
 /* Length (in doubles) of the `out` vector of lcgp_nll_grad:
@@ -69,6 +75,8 @@ size_t lcgp_out_len(int32_t p, int32_t d, int32_t q_loc);
 
 /* Bytes of workspace needed by lcgp_nll_grad / lcgp_predict for a problem of this size. */
 size_t lcgp_workspace_bytes(int32_t n, int32_t d, int32_t p, int32_t q_loc);
+/* Same for a batch of n_emu emulators with q_per latents each (lcgp_problem.n_emu > 1). */
+size_t lcgp_workspace_bytes_batched(int32_t n, int32_t d, int32_t p, int32_t q_per, int32_t n_emu);
 /* Bytes of scratch needed by lcgp_predict for n0 test points. */
 size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
 
@@ -130,6 +138,16 @@ int lcgp_predict(const lcgp_problem* prob, const double* lLmb, const double* lLm
                  void* workspace, size_t workspace_bytes, const double* x0s, int32_t n0, int32_t same_inputs,
                  void* scratch, size_t scratch_bytes, double* ghat /* q_loc x n0 */, double* gvar /* q_loc x n0 */,
                  void* stream);
+
+/* Output maps of predict_rep (lcgp.py:915-926) / predict_full (lcgp.py:840-848) on the device: from the latent
+ * moments ghat, gvar (q x n0, ALL q latents) to the p outputs,
+ *   predmean = Psi ghat, confvar = Psi^2 gvar (element-wise squares), predvar = confvar + noise_var,
+ *   ypred = predmean * scale + shift, yconfvar = confvar * scale^2, ypredvar = predvar * scale^2    (each p x n0).
+ * Psi (p x q) = phi * sqrt(sigma^2_used) per row, noise_var (p) = sigma^2_used, scale / shift (p, may be NULL = 1 / 0)
+ * = ybar_std / ybar_mean (rep) or ystd / ymean (full).  All device pointers. */
+int lcgp_predict_outputs(const double* Psi, const double* ghat, const double* gvar, const double* noise_var,
+                         const double* scale, const double* shift, int32_t p, int32_t q, int32_t n0, double* ypred,
+                         double* ypredvar, double* yconfvar, void* stream);
 
 /* Full predictive covariance of the p outputs at each of n0 test points (predict_full with
  * return_fullcov=True, lcgp.py:850-857):

@@ -21,9 +21,10 @@ _dp = C.c_void_p  # device / host pointers travel as integers
 class Problem(C.Structure):
     """struct lcgp_problem."""
     _fields_ = [('n', C.c_int32), ('d', C.c_int32), ('p', C.c_int32), ('q_loc', C.c_int32),
-                ('include_host_terms', C.c_int32), ('reserved', C.c_int32),
+                ('include_host_terms', C.c_int32), ('n_emu', C.c_int32),
                 ('scale', C.c_double), ('sum_log_r', C.c_double),
-                ('X', _dp), ('sr', _dp), ('YR', _dp), ('w', _dp), ('t', _dp), ('phi', _dp), ('D', _dp)]
+                ('X', _dp), ('sr', _dp), ('YR', _dp), ('w', _dp), ('t', _dp), ('phi', _dp), ('D', _dp),
+                ('emu_consts', _dp)]
 
 
 _SIGS = {
@@ -31,6 +32,7 @@ _SIGS = {
     'lcgp_launch_count': (C.c_ulonglong, []),
     'lcgp_out_len': (C.c_size_t, [C.c_int32] * 3),
     'lcgp_workspace_bytes': (C.c_size_t, [C.c_int32] * 4),
+    'lcgp_workspace_bytes_batched': (C.c_size_t, [C.c_int32] * 5),
     'lcgp_predict_scratch_bytes': (C.c_size_t, [C.c_int32] * 3),
     'lcgp_nll_grad': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp, _dp, C.c_int32,
                                 C.POINTER(C.c_void_p), _dp]),
@@ -42,6 +44,7 @@ _SIGS = {
     'lcgp_plan_destroy': (None, [C.c_void_p]),
     'lcgp_predict': (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_size_t, _dp, C.c_int32, C.c_int32,
                                _dp, C.c_size_t, _dp, _dp, _dp]),
+    'lcgp_predict_outputs': (C.c_int, [_dp, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp]),
     'lcgp_predict_fullcov': (C.c_int, [_dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     'lcgp_prep_segment_mean': (C.c_int, [_dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     'lcgp_prep_row_select': (C.c_int, [_dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),

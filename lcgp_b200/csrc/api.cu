@@ -118,9 +118,11 @@ static inline size_t al(size_t x) { return (x + 31) / 32 * 32; }
 static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)4 * nb * g0; }
 static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)4 * nb * q; }
 
-static Workspace layout(int n, int d, int p, int q, void* basep) {
+// q = all latents of the call (E emulators x q / E latents each)
+static Workspace layout(int n, int d, int p, int q, int E, void* basep) {
     Workspace w;
     w.n = n; w.d = d; w.p = p; w.q = q;
+    if (E < 1) E = 1;
     w.np = round_up(n, NB);
     w.nb = w.np / NB;
     w.ntiles = w.nb * (w.nb + 1) / 2;
@@ -148,8 +150,8 @@ static Workspace layout(int n, int d, int p, int q, void* basep) {
     w.ell = take((size_t)q * d);
     w.s0 = take((size_t)q);
     w.lnug = take((size_t)q);
-    w.lsig = take((size_t)p);
-    w.out = take(lcgp_out_len(p, d, q));
+    w.lsig = take((size_t)E * p);
+    w.out = take((size_t)E * lcgp_out_len(p, d, q / E));
     w.info = (int32_t*)take((size_t)(q + 1) / 2 + 1);
     w.sync = (int*)take((sync_ints(w.nb, q) + 1) / 2);
     w.total_doubles = o;
@@ -164,10 +166,11 @@ static FactorView view_of(const Workspace& w) {
 
 // ---- glue kernels -----------------------------------------------------------------------------
 // V[j][k] = s_j phi[j][k],  s_j = exp(-lsig_j / 2) t_j        (sigma_inv_sqrt * phi[:, k], lcgp.py:608)
-__global__ void prep_v_kernel(int p, int q, const double* __restrict__ lsig, const double* __restrict__ t,
+// (E emulators: V, phi are [E][p][q], lsig, t are [E][p]; idx / q is the flat (e, j) index)
+__global__ void prep_v_kernel(int pE, int q, const double* __restrict__ lsig, const double* __restrict__ t,
                               const double* __restrict__ phi, double* __restrict__ V) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p * q) return;
+    if (idx >= pE * q) return;
     const int j = idx / q;
     V[idx] = exp(-0.5 * lsig[j]) * t[j] * phi[idx];
 }
@@ -175,11 +178,17 @@ __global__ void prep_v_kernel(int p, int q, const double* __restrict__ lsig, con
 // bpart[js][k][i] = sum_{j in slice js} V[j][k] YR[j][i]      (b_k = r * ybar^T v_k, lcgp.py:609-610)
 template <int KC>
 __global__ void __launch_bounds__(128)
-bmat_part_kernel(int n, int np, int p, int q, const double* __restrict__ V, const double* __restrict__ YR,
+// q = latents per emulator, qtot = all latents; blockIdx.z = (emulator, chunk of KC latents of that emulator)
+bmat_part_kernel(int n, int np, int p, int q, int qtot, const double* __restrict__ V, const double* __restrict__ YR,
                  double* __restrict__ bpart) {
     const int i = blockIdx.x * 128 + threadIdx.x;
     const int js = blockIdx.y;
-    const int k0 = blockIdx.z * KC;
+    const int chunks = (q + KC - 1) / KC;
+    const int e = blockIdx.z / chunks;
+    const int k0 = (blockIdx.z % chunks) * KC;
+    V += (size_t)e * p * q;
+    YR += (size_t)e * p * n;
+    bpart += (size_t)e * q * np;
     const int jper = (p + JSPLIT - 1) / JSPLIT;
     const int j0 = js * jper, j1 = min(p, j0 + jper);
     double acc[KC];
@@ -196,7 +205,7 @@ bmat_part_kernel(int n, int np, int p, int q, const double* __restrict__ V, cons
     if (i < np) {
 #pragma unroll
         for (int c = 0; c < KC; ++c)
-            if (k0 + c < q) bpart[((size_t)js * q + k0 + c) * np + i] = acc[c];
+            if (k0 + c < q) bpart[((size_t)js * qtot + k0 + c) * np + i] = acc[c];
     }
 }
 
@@ -216,7 +225,12 @@ zmat_kernel(int n, int np, int p, int q, const double* __restrict__ YR, const do
             double* __restrict__ Z) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
-    const int k0 = blockIdx.y * KC;
+    const int chunks = (q + KC - 1) / KC;             // q = latents per emulator; blockIdx.y = (emulator, chunk)
+    const int e = blockIdx.y / chunks;
+    const int k0 = (blockIdx.y % chunks) * KC;
+    YR += (size_t)e * p * n;
+    mk += (size_t)e * q * np;
+    Z += (size_t)e * p * q;
     if (j >= p) return;
     double acc[KC];
 #pragma unroll
@@ -241,7 +255,15 @@ finalize_kernel(lcgp_problem P, int nb, int with_grad, const double* __restrict_
                 const double* __restrict__ Z, double* __restrict__ out) {
     __shared__ double red[8];
     const int tid = threadIdx.x;
-    const int p = P.p, q = P.q_loc, d = P.d;
+    const int E = P.n_emu > 1 ? P.n_emu : 1;
+    const int p = P.p, q = P.q_loc / E, d = P.d;
+    {   // one block per emulator: shift every per-emulator array (the emulators' constants follow each other)
+        const int e = blockIdx.x;
+        lsig += (size_t)e * p; logdet_part += (size_t)e * q * nb; quad += (size_t)e * q; Z += (size_t)e * p * q;
+        out += (size_t)e * (1 + p + (size_t)q * d + 4 * (size_t)q);
+        P.w += (size_t)e * p; P.t += (size_t)e * p; P.phi += (size_t)e * p * q;
+        if (P.n_emu > 1) { P.scale = P.emu_consts[2 * e]; P.sum_log_r = P.emu_consts[2 * e + 1]; }
+    }
     double* g_sig = out + 1;
     double* g_kern = out + 1 + p;                       // q*d + q + q values
     double* diag_logdet = g_kern + (size_t)q * d + 2 * q;
@@ -324,23 +346,26 @@ static int check_problem(const lcgp_problem* P) {
     if (!P || P->n <= 0 || P->d <= 0 || P->p <= 0 || P->q_loc <= 0) return LCGP_E_ARG;
     if (!P->X || !P->sr || !P->YR || !P->w || !P->t || !P->phi || !P->D) return LCGP_E_ARG;
     if (P->d > LCGP_MAX_D) return LCGP_E_DIM;
+    if (P->n_emu < 0 || (P->n_emu > 1 && (P->q_loc % P->n_emu != 0 || !P->emu_consts))) return LCGP_E_ARG;
     return 0;
 }
+static inline int n_emu(const lcgp_problem* P) { return P->n_emu > 1 ? P->n_emu : 1; }
 
 static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double* s0, const double* lnug,
                          const double* lsig, const Workspace& w, double* out, int32_t* info, int flags,
                          void* const* ev, cudaStream_t st) {
     const int n = P->n, d = P->d, p = P->p, q = P->q_loc;
+    const int E = n_emu(P), qe = q / E;             // emulators in this call, latents per emulator
     const int with_grad = flags & 1;
     FactorView v = view_of(w);
-    KernelParams kp{ell, s0, lnug, P->D};
+    KernelParams kp{ell, s0, lnug, P->D, qe};
     auto rec = [&](int i) { if (ev && ev[i]) cudaEventRecord((cudaEvent_t)ev[i], st); };
     rec(0);
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * q, st));
     // b_k
-    note_launch(); prep_v_kernel<<<(p * q + 255) / 256, 256, 0, st>>>(p, q, lsig, P->t, P->phi, w.V);
+    note_launch(); prep_v_kernel<<<(E * p * qe + 255) / 256, 256, 0, st>>>(E * p, qe, lsig, P->t, P->phi, w.V);
     LCGP_CUDA(cudaGetLastError());
-    note_launch(); bmat_part_kernel<8><<<dim3(w.np / 128, JSPLIT, (q + 7) / 8), 128, 0, st>>>(n, w.np, p, q, w.V, P->YR, w.bpart);
+    note_launch(); bmat_part_kernel<8><<<dim3(w.np / 128, JSPLIT, E * ((qe + 7) / 8)), 128, 0, st>>>(n, w.np, p, qe, q, w.V, P->YR, w.bpart);
     LCGP_CUDA(cudaGetLastError());
     note_launch(); bmat_reduce_kernel<<<(unsigned)(((size_t)q * w.np + 255) / 256), 256, 0, st>>>(w.np, q, w.bpart, w.B);
     LCGP_CUDA(cudaGetLastError());
@@ -394,15 +419,15 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     LCGP_CUDA(solve_alpha(v, a, st));
     double* g_kern = out + 1 + p;
     if (with_grad) {
-        LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, g_kern + (size_t)q * d, g_kern + (size_t)q * d + q,
+        LCGP_CUDA(contract_grad(v, a, w.tile_part, g_kern, lcgp_out_len(p, d, qe),
                                 ev ? (cudaEvent_t)ev[4] : nullptr, ev ? (cudaEvent_t)ev[5] : nullptr, st));
-        note_launch(); zmat_kernel<8><<<dim3((p + 7) / 8, (q + 7) / 8), 256, 0, st>>>(n, w.np, p, q, P->YR, w.mk, w.Z);
+        note_launch(); zmat_kernel<8><<<dim3((p + 7) / 8, E * ((qe + 7) / 8)), 256, 0, st>>>(n, w.np, p, qe, P->YR, w.mk, w.Z);
         LCGP_CUDA(cudaGetLastError());
     } else {
         rec(4);
         rec(5);
     }
-    note_launch(); finalize_kernel<<<1, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
+    note_launch(); finalize_kernel<<<E, 256, 0, st>>>(*P, w.nb, with_grad, lsig, w.logdet_part, w.quad, w.Z, out);
     LCGP_CUDA(cudaGetLastError());
     rec(6);
     return 0;
@@ -424,7 +449,13 @@ size_t lcgp_out_len(int32_t p, int32_t d, int32_t q_loc) {
 
 size_t lcgp_workspace_bytes(int32_t n, int32_t d, int32_t p, int32_t q_loc) {
     if (n <= 0 || d <= 0 || p <= 0 || q_loc <= 0) return 0;
-    Workspace w = layout(n, d, p, q_loc, nullptr);
+    Workspace w = layout(n, d, p, q_loc, 1, nullptr);
+    return w.total_doubles * sizeof(double);
+}
+
+size_t lcgp_workspace_bytes_batched(int32_t n, int32_t d, int32_t p, int32_t q_per, int32_t n_emu) {
+    if (n <= 0 || d <= 0 || p <= 0 || q_per <= 0 || n_emu <= 0) return 0;
+    Workspace w = layout(n, d, p, q_per * n_emu, n_emu, nullptr);
     return w.total_doubles * sizeof(double);
 }
 
@@ -440,7 +471,7 @@ int lcgp_nll_grad(const lcgp_problem* P, const double* lLmb, const double* lLmb0
     int rc = check_problem(P);
     if (rc) return rc;
     if (!lLmb || !lLmb0 || !lnugGPs || !lsigma2_p || !workspace || !out || !info) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     return nll_grad_impl(P, lLmb, lLmb0, lnugGPs, lsigma2_p, w, out, info, flags, stage_events, (cudaStream_t)stream);
 }
@@ -451,17 +482,18 @@ int lcgp_nll_grad_host(const lcgp_problem* P, const double* lLmb_h, const double
     int rc = check_problem(P);
     if (rc) return rc;
     if (!lLmb_h || !lLmb0_h || !lnug_h || !lsig_h || !workspace || !out_h || !info_h) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int q = P->q_loc;
     LCGP_CUDA(cudaMemcpyAsync(w.ell, lLmb_h, sizeof(double) * q * P->d, cudaMemcpyHostToDevice, st));
     LCGP_CUDA(cudaMemcpyAsync(w.s0, lLmb0_h, sizeof(double) * q, cudaMemcpyHostToDevice, st));
     LCGP_CUDA(cudaMemcpyAsync(w.lnug, lnug_h, sizeof(double) * q, cudaMemcpyHostToDevice, st));
-    LCGP_CUDA(cudaMemcpyAsync(w.lsig, lsig_h, sizeof(double) * P->p, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lsig, lsig_h, sizeof(double) * n_emu(P) * P->p, cudaMemcpyHostToDevice, st));
     rc = nll_grad_impl(P, w.ell, w.s0, w.lnug, w.lsig, w, w.out, w.info, flags, stage_events, st);
     if (rc) return rc;
-    LCGP_CUDA(cudaMemcpyAsync(out_h, w.out, sizeof(double) * lcgp_out_len(P->p, P->d, q), cudaMemcpyDeviceToHost, st));
+    LCGP_CUDA(cudaMemcpyAsync(out_h, w.out, sizeof(double) * n_emu(P) * lcgp_out_len(P->p, P->d, q / n_emu(P)),
+                              cudaMemcpyDeviceToHost, st));
     LCGP_CUDA(cudaMemcpyAsync(info_h, w.info, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
     LCGP_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -492,15 +524,16 @@ struct lcgp_plan {
 static int plan_enqueue(const lcgp_plan* pl, cudaStream_t st) {
     const lcgp_problem* P = &pl->prob;
     const int q = P->q_loc, d = P->d, p = P->p;
-    Workspace w = layout(P->n, d, p, q, pl->ws);
+    const int E = n_emu(P);
+    Workspace w = layout(P->n, d, p, q, E, pl->ws);
     const double* h = pl->par_h;
     LCGP_CUDA(cudaMemcpyAsync(w.ell, h, sizeof(double) * q * d, cudaMemcpyHostToDevice, st));
     LCGP_CUDA(cudaMemcpyAsync(w.s0, h + (size_t)q * d, sizeof(double) * q, cudaMemcpyHostToDevice, st));
     LCGP_CUDA(cudaMemcpyAsync(w.lnug, h + (size_t)q * d + q, sizeof(double) * q, cudaMemcpyHostToDevice, st));
-    LCGP_CUDA(cudaMemcpyAsync(w.lsig, h + (size_t)q * d + 2 * q, sizeof(double) * p, cudaMemcpyHostToDevice, st));
+    LCGP_CUDA(cudaMemcpyAsync(w.lsig, h + (size_t)q * d + 2 * q, sizeof(double) * E * p, cudaMemcpyHostToDevice, st));
     int rc = nll_grad_impl(P, w.ell, w.s0, w.lnug, w.lsig, w, w.out, w.info, pl->flags, nullptr, st);
     if (rc) return rc;
-    LCGP_CUDA(cudaMemcpyAsync(pl->out_h, w.out, sizeof(double) * lcgp_out_len(p, d, q), cudaMemcpyDeviceToHost, st));
+    LCGP_CUDA(cudaMemcpyAsync(pl->out_h, w.out, sizeof(double) * E * lcgp_out_len(p, d, q / E), cudaMemcpyDeviceToHost, st));
     LCGP_CUDA(cudaMemcpyAsync(pl->info_h, w.info, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
     return 0;
 }
@@ -512,7 +545,7 @@ int lcgp_plan_create(const lcgp_problem* P, void* workspace, size_t workspace_by
     int rc = check_problem(P);
     if (rc) return rc;
     if (!workspace || !params_host || !out_host || !info_host || !plan) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     lcgp_plan* pl = new (std::nothrow) lcgp_plan();
     if (!pl) return LCGP_E_ARG;
@@ -586,12 +619,22 @@ int lcgp_predict(const lcgp_problem* P, const double* lLmb, const double* lLmb0,
     int rc = check_problem(P);
     if (rc) return rc;
     if (!lLmb || !lLmb0 || !lnugGPs || !workspace || !x0s || n0 <= 0 || !scratch || !ghat || !gvar) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     if (scratch_bytes < lcgp_predict_scratch_bytes(P->n, P->q_loc, n0)) return LCGP_E_WORKSPACE;
-    KernelParams kp{lLmb, lLmb0, lnugGPs, P->D};
+    if (n_emu(P) > 1) return LCGP_E_ARG;            // prediction works on one emulator (build it from the fitted parameters)
+    KernelParams kp{lLmb, lLmb0, lnugGPs, P->D, P->q_loc};
     return cuda_rc(predict_latents(view_of(w), P->n, P->d, P->X, P->sr, kp, w.atil, x0s, n0, same_inputs,
                                    (double*)scratch, P->q_loc, ghat, gvar, (cudaStream_t)stream));
+}
+
+int lcgp_predict_outputs(const double* Psi, const double* ghat, const double* gvar, const double* noise_var,
+                         const double* scale, const double* shift, int32_t p, int32_t q, int32_t n0, double* ypred,
+                         double* ypredvar, double* yconfvar, void* stream) {
+    if (!Psi || !ghat || !gvar || !noise_var || !ypred || !ypredvar || !yconfvar || p <= 0 || q <= 0 || n0 <= 0) return LCGP_E_ARG;
+    if ((size_t)q * 8 * sizeof(double) > 200 * 1024) return LCGP_E_DIM;
+    return cuda_rc(launch_predict_outputs(Psi, ghat, gvar, noise_var, scale, shift, p, q, n0, ypred, ypredvar, yconfvar,
+                                          (cudaStream_t)stream));
 }
 
 int lcgp_predict_fullcov(const double* psi, const double* gvar, const double* sig2, const double* ystd, int32_t q,
@@ -622,8 +665,8 @@ int lcgp_grad_phi(const lcgp_problem* P, const double* lsigma2_p, void* workspac
                   void* stream) {
     int rc = check_problem(P);
     if (rc) return rc;
-    if (!lsigma2_p || !workspace || !g_phi) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    if (!lsigma2_p || !workspace || !g_phi || n_emu(P) > 1) return LCGP_E_ARG;
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     // scratch: the GEMV partial-sum area, free once lcgp_nll_grad has finished
     return cuda_rc(grad_phi(view_of(w), P->n, P->p, P->q_loc, P->scale, P->sr, w.mk, lsigma2_p, P->t, P->phi, P->D, w.Z,
@@ -643,7 +686,7 @@ int lcgp_get_aux(const lcgp_problem* P, void* workspace, size_t workspace_bytes,
     int rc = check_problem(P);
     if (rc) return rc;
     if (!workspace || !CinvMs || !mks) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t rowb = sizeof(double) * P->n;
@@ -691,7 +734,7 @@ int lcgp_get_Ainv(const lcgp_problem* P, void* workspace, size_t workspace_bytes
     int rc = check_problem(P);
     if (rc) return rc;
     if (!workspace || !Ainv || k < 0 || k >= P->q_loc) return LCGP_E_ARG;
-    Workspace w = layout(P->n, P->d, P->p, P->q_loc, workspace);
+    Workspace w = layout(P->n, P->d, P->p, P->q_loc, n_emu(P), workspace);
     if (workspace_bytes < w.total_doubles * sizeof(double)) return LCGP_E_WORKSPACE;
     const int g = (P->n + 15) / 16;
     note_launch(); ainv_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(view_of(w), k, P->n, Ainv);
@@ -710,7 +753,7 @@ int lcgp_build_A(const double* X, const double* sr, int32_t n, int32_t d, const 
                  const double* lnugGPs, const double* D, int32_t batch, double* F, int32_t np, void* stream) {
     if (!X || !sr || !lLmb || !lLmb0 || !lnugGPs || !D || !F || n <= 0 || d <= 0 || batch <= 0) return LCGP_E_ARG;
     if (d > LCGP_MAX_D || np % NB != 0 || np < n) return LCGP_E_DIM;
-    KernelParams kp{lLmb, lLmb0, lnugGPs, D};
+    KernelParams kp{lLmb, lLmb0, lnugGPs, D, batch};
     return cuda_rc(launch_build_A(X, sr, n, d, np, kp, F, (size_t)np * np, batch, (cudaStream_t)stream));
 }
 

@@ -37,6 +37,8 @@ struct KernelParams {
     const double* s0;
     const double* lnug;
     const double* D;  // diag_D of the local latents
+    int q_per;        // latents per emulator: latent k belongs to emulator k / q_per, whose X / sr / YR / ... follow
+                      // those of emulator 0 at the natural strides (one emulator: q_per = q_loc)
 };
 
 // matern.cu
@@ -61,8 +63,9 @@ struct SolveArgs {
     double* quad;        // q_loc out: b^T m
 };
 cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream);
+// g_kern: kernel-gradient part of emulator 0's out block; emulator e's follows at e * out_stride doubles
 cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part /* q_loc x ntiles x (d+2) */,
-                          double* g_ell, double* g_s0, double* g_lnug, cudaEvent_t ev_before, cudaEvent_t ev_after,
+                          double* g_kern, size_t out_stride, cudaEvent_t ev_before, cudaEvent_t ev_after,
                           cudaStream_t stream);
 
 cudaError_t grad_phi(const FactorView& v, int n, int p, int q_loc, double scale, const double* sr, const double* mk,
@@ -73,6 +76,10 @@ cudaError_t grad_phi(const FactorView& v, int n, int p, int q_loc, double scale,
 cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,
                             const double* atil, const double* x0s, int n0, int same, double* scratch,
                             int q_loc, double* ghat, double* gvar, cudaStream_t stream);
+
+cudaError_t launch_predict_outputs(const double* Psi, const double* ghat, const double* gvar, const double* noise_var,
+                                   const double* scale, const double* shift, int p, int q, int n0, double* ypred,
+                                   double* ypredvar, double* yconfvar, cudaStream_t stream);
 
 // fullcov.cu
 cudaError_t launch_fullcov(const double* psi, const double* gvar, const double* sig2, const double* sv, int q, int p,

@@ -22,6 +22,11 @@ build_A_kernel(const double* __restrict__ X, const double* __restrict__ sr, int 
     double* xi = sm;           // [d][64]
     double* xj = sm + d * MT;  // [d][64]
     const int k = blockIdx.y;
+    {   // this latent's emulator
+        const int e = k / kp.q_per;
+        X += (size_t)e * n * d;
+        sr += (size_t)e * n;
+    }
     int TI, TJ;
     tri_decode(blockIdx.x, TI, TJ);
     const int i0 = TI * MT, j0 = TJ * MT;

@@ -78,6 +78,64 @@ predict_finish_kernel(int np, int nb, int n0, int n0p, const double* __restrict_
     }
 }
 
+// ---- output maps (lcgp.py:915-926 rep, :840-848 full): from the latent moments to the p outputs, on the device ----
+//   predmean = Psi ghat,  confvar = Psi^2 gvar,  predvar = confvar + noise_var
+//   ypred = predmean * scale + shift,  yconfvar = confvar * scale^2,  ypredvar = predvar * scale^2
+// One thread per test point and 8 outputs; Psi rows of the block in shared memory; ghat / gvar columns stream
+// through L2 (q x n0 each, re-read by every block of outputs).
+constexpr int PO_J = 8;
+__global__ void __launch_bounds__(128)
+predict_outputs_kernel(int p, int q, int n0, const double* __restrict__ Psi, const double* __restrict__ ghat,
+                       const double* __restrict__ gvar, const double* __restrict__ noise_var,
+                       const double* __restrict__ scale, const double* __restrict__ shift,
+                       double* __restrict__ ypred, double* __restrict__ ypredvar, double* __restrict__ yconfvar) {
+    extern __shared__ double ps[];      // [PO_J][q]
+    const int j0 = blockIdx.y * PO_J;
+    for (int idx = threadIdx.x; idx < PO_J * q; idx += blockDim.x) {
+        const int jj = idx / q, k = idx % q;
+        ps[idx] = (j0 + jj < p) ? Psi[(size_t)(j0 + jj) * q + k] : 0.0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    double m[PO_J], c[PO_J];
+#pragma unroll
+    for (int jj = 0; jj < PO_J; ++jj) m[jj] = c[jj] = 0.0;
+    for (int k = 0; k < q; ++k) {
+        const double gh = ghat[(size_t)k * n0 + i], gv = gvar[(size_t)k * n0 + i];
+#pragma unroll
+        for (int jj = 0; jj < PO_J; ++jj) {
+            const double w = ps[jj * q + k];
+            m[jj] = fma(w, gh, m[jj]);
+            c[jj] = fma(w * w, gv, c[jj]);
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < PO_J; ++jj) {
+        const int j = j0 + jj;
+        if (j >= p) break;
+        const double sc = scale ? scale[j] : 1.0, sh = shift ? shift[j] : 0.0;
+        const size_t o = (size_t)j * n0 + i;
+        ypred[o] = m[jj] * sc + sh;
+        yconfvar[o] = c[jj] * (sc * sc);
+        ypredvar[o] = (c[jj] + noise_var[j]) * (sc * sc);
+    }
+}
+
+cudaError_t launch_predict_outputs(const double* Psi, const double* ghat, const double* gvar, const double* noise_var,
+                                   const double* scale, const double* shift, int p, int q, int n0, double* ypred,
+                                   double* ypredvar, double* yconfvar, cudaStream_t stream) {
+    const size_t smem = sizeof(double) * PO_J * q;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(predict_outputs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    note_launch();
+    predict_outputs_kernel<<<dim3((n0 + 127) / 128, (p + PO_J - 1) / PO_J), 128, smem, stream>>>(
+        p, q, n0, Psi, ghat, gvar, noise_var, scale, shift, ypred, ypredvar, yconfvar);
+    return cudaGetLastError();
+}
+
 cudaError_t predict_latents(const FactorView& v, int n, int d, const double* X, const double* sr, KernelParams kp,
                             const double* atil, const double* x0s, int n0, int same, double* scratch,
                             int q_loc, double* ghat, double* gvar, cudaStream_t stream) {

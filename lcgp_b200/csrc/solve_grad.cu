@@ -17,10 +17,11 @@ namespace lcgp {
 
 // ---- y = U^T v :  y[k] = sum_{i <= k} U[i][k] v[i] -----------------------------------------------
 __global__ void __launch_bounds__(NB)
-gemv_ut_part_kernel(FactorView v, const double* __restrict__ B, const double* __restrict__ sr, int n,
+gemv_ut_part_kernel(FactorView v, const double* __restrict__ B, const double* __restrict__ sr, int n, int q_per,
                     double* __restrict__ part /* [batch][nb][np] */) {
     const int Kb = blockIdx.x, Ib = blockIdx.y, bz = blockIdx.z;
     if (Ib > Kb) return;
+    sr += (size_t)(bz / q_per) * n;
     __shared__ double vs[NB];
     const int c = threadIdx.x;
     {
@@ -56,12 +57,13 @@ __global__ void gemv_ut_reduce_kernel(int np, int nb, const double* __restrict__
 // ---- atil = U y (one warp per row), then alpha, m ----------------------------------------------
 __global__ void __launch_bounds__(256)
 gemv_u_kernel(FactorView v, const double* __restrict__ y, const double* __restrict__ B,
-              const double* __restrict__ sr, const double* __restrict__ Dk, int n,
+              const double* __restrict__ sr, const double* __restrict__ Dk, int n, int q_per,
               double* __restrict__ atil, double* __restrict__ alpha, double* __restrict__ mk) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
     const int bz = blockIdx.y;
     if (i >= v.np) return;
+    sr += (size_t)(bz / q_per) * n;
     const int I = i / NB, il = i % NB;
     const double* yk = y + (size_t)bz * v.np;
     const double* durow = v.DU + (size_t)bz * v.dstride + (size_t)I * NB * NB + (size_t)il * NB;
@@ -98,15 +100,15 @@ quad_kernel(int np, const double* __restrict__ B, const double* __restrict__ mk,
 
 // gemv_part holds q_loc * nb * np partial sums followed by q_loc * np doubles for y = U^T v.
 cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t stream) {
-    note_launch(); gemv_ut_part_kernel<<<dim3(v.nb, v.nb, a.q_loc), NB, 0, stream>>>(v, a.B, a.sr, a.n, a.gemv_part);
+    note_launch(); gemv_ut_part_kernel<<<dim3(v.nb, v.nb, a.q_loc), NB, 0, stream>>>(v, a.B, a.sr, a.n, a.kp.q_per, a.gemv_part);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     double* ybuf = a.gemv_part + (size_t)a.q_loc * v.nb * v.np;
     note_launch(); gemv_ut_reduce_kernel<<<dim3((v.np + 255) / 256, a.q_loc), 256, 0, stream>>>(v.np, v.nb, a.gemv_part, ybuf);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    note_launch(); gemv_u_kernel<<<dim3((v.np + 7) / 8, a.q_loc), 256, 0, stream>>>(v, ybuf, a.B, a.sr, a.kp.D, a.n, a.atil,
-                                                                      a.alpha, a.mk);
+    note_launch(); gemv_u_kernel<<<dim3((v.np + 7) / 8, a.q_loc), 256, 0, stream>>>(v, ybuf, a.B, a.sr, a.kp.D, a.n, a.kp.q_per,
+                                                                      a.atil, a.alpha, a.mk);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     note_launch(); quad_kernel<<<a.q_loc, 256, 0, stream>>>(v.np, a.B, a.mk, a.quad);
@@ -164,17 +166,19 @@ struct ContractJob {
         double* aj = ai + NB;
         double* red = aj + NB;             // [(d + 2)][8]
         const double* ell = p.kp.ell + (size_t)k * d;
+        const double* Xe = p.X + (size_t)(k / p.kp.q_per) * n * d;      // this latent's emulator
+        const double* sre = p.sr + (size_t)(k / p.kp.q_per) * n;
         for (int idx = tid; idx < NB * d; idx += GEMM_THREADS) {
             const int m = idx / NB, r = idx % NB;
             const int gi = I * NB + r, gj = J * NB + r;
             const double l = ell[m];
-            xi[idx] = gi < n ? p.X[(size_t)gi * d + m] / l : 0.0;
-            xj[idx] = gj < n ? p.X[(size_t)gj * d + m] / l : 0.0;
+            xi[idx] = gi < n ? Xe[(size_t)gi * d + m] / l : 0.0;
+            xj[idx] = gj < n ? Xe[(size_t)gj * d + m] / l : 0.0;
         }
         if (tid < NB) {
             const int gi = I * NB + tid, gj = J * NB + tid;
-            sri[tid] = gi < n ? p.sr[gi] : 0.0;
-            srj[tid] = gj < n ? p.sr[gj] : 0.0;
+            sri[tid] = gi < n ? sre[gi] : 0.0;
+            srj[tid] = gj < n ? sre[gj] : 0.0;
             ai[tid] = p.alpha[(size_t)k * p.v.np + gi];
             aj[tid] = p.alpha[(size_t)k * p.v.np + gj];
         }
@@ -254,21 +258,23 @@ struct ContractJob {
     }
 };
 
-__global__ void contract_reduce_kernel(int ntiles, int d, const double* __restrict__ tile_part,
-                                       double* __restrict__ g_ell, double* __restrict__ g_s0,
-                                       double* __restrict__ g_lnug) {
+// g_kern: the kernel-gradient part of emulator 0's `out` block ([d/d lLmb (q_per x d) | d/d lLmb0 (q_per) | d/d lnugGPs
+// (q_per)]); emulator e's block follows at e * out_stride
+__global__ void contract_reduce_kernel(int ntiles, int d, int q_per, size_t out_stride, const double* __restrict__ tile_part,
+                                       double* __restrict__ g_kern) {
     const int k = blockIdx.x, c = threadIdx.x;
     if (c >= d + 2) return;
     double s = 0.0;
     for (int t = 0; t < ntiles; ++t) s += tile_part[((size_t)k * ntiles + t) * (d + 2) + c];
-    if (c == 0) g_s0[k] = s;
-    else if (c == 1) g_lnug[k] = s;
-    else g_ell[(size_t)k * d + (c - 2)] = s;
+    const int kk = k % q_per;
+    double* g = g_kern + (size_t)(k / q_per) * out_stride;
+    if (c == 0) g[(size_t)q_per * d + kk] = s;
+    else if (c == 1) g[(size_t)q_per * d + q_per + kk] = s;
+    else g[(size_t)kk * d + (c - 2)] = s;
 }
 
-cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part, double* g_ell,
-                          double* g_s0, double* g_lnug, cudaEvent_t ev_before, cudaEvent_t ev_after,
-                          cudaStream_t stream) {
+cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_part, double* g_kern, size_t out_stride,
+                          cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream) {
     const int ntiles = v.nb * (v.nb + 1) / 2;
     ContractParams p{v, a.n, a.d, a.X, a.sr, a.alpha, a.kp, tile_part, ntiles};
     GemmCtx ctx;
@@ -283,7 +289,7 @@ cudaError_t contract_grad(const FactorView& v, const SolveArgs& a, double* tile_
     cudaError_t e = gemm_launch<ContractJob>(ctx, p, dim3(ntiles, a.q_loc, 1), stream);
     if (ev_after) cudaEventRecord(ev_after, stream);
     if (e != cudaSuccess) return e;
-    note_launch(); contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, tile_part, g_ell, g_s0, g_lnug);
+    note_launch(); contract_reduce_kernel<<<a.q_loc, round_up(a.d + 2, 32), 0, stream>>>(ntiles, a.d, a.kp.q_per, out_stride, tile_part, g_kern);
     return cudaGetLastError();
 }
 

@@ -90,7 +90,7 @@ class CudaEngine:
         self.X, self.sr, self.YR, self.w, self.t = c(X), c(sr), c(YR), c(w), c(t)
         self.phi, self.D = c(phi_loc), c(D_loc)
         self.prob = _cabi.Problem(n=self.n, d=self.d, p=self.p, q_loc=self.q_loc,
-                                  include_host_terms=int(bool(include_host_terms)), reserved=0,
+                                  include_host_terms=int(bool(include_host_terms)), n_emu=0, emu_consts=None,
                                   scale=float(scale), sum_log_r=float(sum_log_r),
                                   X=self.X.data_ptr(), sr=self.sr.data_ptr(), YR=self.YR.data_ptr(),
                                   w=self.w.data_ptr(), t=self.t.data_ptr(), phi=self.phi.data_ptr(),
@@ -351,8 +351,8 @@ class LCGP:
         self._local_idx = torch.arange(self.q)[self._rank::self._world]   # empty when this rank owns no latent
 
         self._invalidate_aux()
-        self.ghat = None
-        self.gvar = None
+        self._ghat = self._gvar = None          # latent predictive moments of the last predict(): CPU copies made on demand
+        self._ghat_dev = self._gvar_dev = None
         self.psi_c = None
         self.n_evals = 0
 
@@ -965,7 +965,27 @@ class LCGP:
         res = call(x0=x0, return_fullcov=return_fullcov)
         return tuple(t.detach() if t is not None else None for t in res)
 
-    def _predict_latents(self, x0, Xtrain, chunk=2048):
+    def _gather_latent_moments(self, gh, gv, width):
+        """This rank's (q_loc x width) latent means / variances -> the full (q x width) pair ON THE DEVICE of the
+        collective: ONE all_gather of the stacked pair (rows padded to the largest q_loc) instead of two all-reduces."""
+        q = int(self.q)
+        if self._world == 1:
+            return gh, gv
+        W = self._world
+        dev = self._collective_device()
+        qmax = -(-q // W)
+        loc = torch.zeros((2, qmax, width), dtype=DT, device=dev)
+        if gh is not None:
+            loc[0, :gh.shape[0]] = gh.to(dev)
+            loc[1, :gv.shape[0]] = gv.to(dev)
+        allb = torch.empty((W * 2, qmax, width), dtype=DT, device=dev)      # concatenation along dim 0 (gloo wants that shape)
+        torch.distributed.all_gather_into_tensor(allb, loc)
+        allb = allb.view(W, 2, qmax, width)
+        k = torch.arange(q, device=dev)
+        full = allb[k % W, :, k // W]                      # latent k lives on rank k % W at local row k // W
+        return full[:, 0].contiguous(), full[:, 1].contiguous()
+
+    def _predict_latents(self, x0, Xtrain, chunk=2048, keep_on_device=False):
         if self._aux_is_stale():
             self.compute_aux_predictive_quantities()
         lLmb, lLmb0, lsig_p, lnug = self._refresh_factor()
@@ -982,48 +1002,92 @@ class LCGP:
                 a, b = eng.predict_latents(lLmb[idx], lLmb0[idx], lnug[idx], x0s[s:s + chunk].contiguous(), same)
             else:
                 a = b = None
-            w = min(chunk, n0 - s)
-            gh.append(self._gather_rows(a, w))
-            gv.append(self._gather_rows(b, w))
-        self.ghat = torch.cat(gh, dim=1)
-        self.gvar = torch.cat(gv, dim=1)
+            a, b = self._gather_latent_moments(a, b, min(chunk, n0 - s))
+            gh.append(a)
+            gv.append(b)
+        ghat_d = gh[0] if len(gh) == 1 else torch.cat(gh, dim=1)
+        gvar_d = gv[0] if len(gv) == 1 else torch.cat(gv, dim=1)
+        self._ghat_dev, self._gvar_dev = ghat_d, gvar_d
+        self._ghat = self._gvar = None                    # CPU copies on demand (properties ghat / gvar)
+        if keep_on_device and ghat_d.is_cuda:
+            return ghat_d, gvar_d, lsig_p
         return self.ghat, self.gvar, lsig_p
+
+    def _latent_moments_host(self):
+        """ghat / gvar (q x n0) of the last prediction as CPU tensors (reference attributes, lcgp.py:899-900)."""
+        if self._ghat is None and self._ghat_dev is not None:
+            self._ghat, self._gvar = self._ghat_dev.cpu(), self._gvar_dev.cpu()
+        return self._ghat, self._gvar
+
+    @property
+    def ghat(self):
+        return self._latent_moments_host()[0]
+
+    @ghat.setter
+    def ghat(self, v):
+        self._ghat, self._ghat_dev = v, None
+
+    @property
+    def gvar(self):
+        return self._latent_moments_host()[1]
+
+    @gvar.setter
+    def gvar(self, v):
+        self._gvar, self._gvar_dev = v, None
+
+    def _output_maps(self, Psi, ghat, gvar, noise_var, scale, shift):
+        """lcgp.py:915-926 / :840-848: (ypred, ypredvar, yconfvar), each p x n0, as CPU tensors.  With the latent moments
+        on a CUDA device the three products and the un-standardisation run there (lcgp_predict_outputs) and only the
+        results come back (pinned host memory); otherwise (test engines on the CPU) in torch on the host."""
+        p, q, n0 = int(self.p), int(self.q), int(ghat.shape[1])
+        if ghat.is_cuda and _cabi.available():
+            dev = ghat.device
+            c = lambda t: None if t is None else t.to(dev, DT).contiguous()
+            Psi_d, nv_d, sc_d, sh_d = c(Psi), c(noise_var), c(scale), c(shift)
+            outs = [torch.empty((p, n0), dtype=DT, device=dev) for _ in range(3)]
+            ptr = lambda t: None if t is None else t.data_ptr()
+            with torch.cuda.device(dev):
+                rc = _cabi.lib().lcgp_predict_outputs(Psi_d.data_ptr(), ghat.data_ptr(), gvar.data_ptr(), nv_d.data_ptr(),
+                                                      ptr(sc_d), ptr(sh_d), p, q, n0, outs[0].data_ptr(), outs[1].data_ptr(),
+                                                      outs[2].data_ptr(), _cabi.stream_ptr())
+                _cabi.check(rc, 'lcgp_predict_outputs')
+                host = [torch.empty((p, n0), dtype=DT, pin_memory=True) for _ in range(3)]
+                for h, o in zip(host, outs):
+                    h.copy_(o, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            return tuple(host)
+        predmean = Psi @ ghat
+        confvar = (Psi ** 2) @ gvar
+        predvar = confvar + noise_var[:, None]
+        sc = torch.ones(p, dtype=DT) if scale is None else scale
+        sh = torch.zeros(p, dtype=DT) if shift is None else shift
+        return predmean * sc[:, None] + sh[:, None], predvar * sc[:, None] ** 2, confvar * sc[:, None] ** 2
 
     def predict_full(self, x0, return_fullcov=False):
         """lcgp.py:808-859."""
-        ghat, gvar, lsig_p = self._predict_latents(x0, self.x)
-        psi = self.phi.T * torch.sqrt(torch.exp(lsig_p))                    # (q, p)
-        predmean = psi.T @ ghat
-        confvar = gvar.T @ psi ** 2
-        predvar = confvar + torch.exp(lsig_p)
-        ypred = self.tx_y(predmean)
-        yconfvar = confvar.T * self.ystd ** 2
-        ypredvar = predvar.T * self.ystd ** 2
+        ghat, gvar, lsig_p = self._predict_latents(x0, self.x, keep_on_device=True)
+        sig2 = torch.exp(lsig_p)
+        Psi = self.phi * torch.sqrt(sig2)[:, None]                          # (p, q) = psi^T of lcgp.py:838
+        ypred, ypredvar, yconfvar = self._output_maps(Psi, ghat, gvar, sig2, self.ystd[:, 0], self.ymean[:, 0])
         if return_fullcov:
             # lcgp.py:850-857: n0 rank-q updates of a diagonal, written by one kernel (csrc/fullcov.cu)
-            full = _fullcov_cuda(psi, gvar, torch.exp(lsig_p), self.ystd[:, 0], self._device)
+            full = _fullcov_cuda(Psi.T.contiguous(), self._latent_moments_host()[1], sig2, self.ystd[:, 0], self._device)
             return ypred, ypredvar, yconfvar, full
         return ypred, ypredvar, yconfvar
 
     def predict_rep(self, x0, return_fullcov=False):
         """lcgp.py:864-930."""
-        ghat, gvar, lsig_p = self._predict_latents(x0, self.x_unique_s)
+        ghat, gvar, lsig_p = self._predict_latents(x0, self.x_unique_s, keep_on_device=True)
         sigma_var = torch.exp(lsig_p)
         sigma_sqrt = torch.sqrt(sigma_var)
+        scale = shift = None
         if self.rep_standardize_ybar:
             std = self.ybar_std[:, 0]
             sigma_sqrt = sigma_sqrt / std
             sigma_var = sigma_var / std ** 2
+            scale, shift = std, self.ybar_mean[:, 0]
         Psi = self.phi * sigma_sqrt[:, None]
-        predmean = Psi @ ghat
-        confvar = (Psi ** 2) @ gvar
-        predvar = confvar + sigma_var[:, None]
-        if self.rep_standardize_ybar:
-            ypred = predmean * self.ybar_std + self.ybar_mean
-            yconfvar = confvar * self.ybar_std ** 2
-            ypredvar = predvar * self.ybar_std ** 2
-        else:
-            ypred, yconfvar, ypredvar = predmean, confvar, predvar
+        ypred, ypredvar, yconfvar = self._output_maps(Psi, ghat, gvar, sigma_var, scale, shift)
         if return_fullcov:
             return ypred, ypredvar, yconfvar, None
         return ypred, ypredvar, yconfvar

@@ -41,7 +41,7 @@ def test_size_queries_without_gpu():
 
 def test_problem_struct_layout():
     # the ctypes mirror must match the C struct: 6 int32, 2 doubles, 7 pointers, no padding surprises
-    assert ctypes.sizeof(_cabi.Problem) == 6 * 4 + 2 * 8 + 7 * 8
+    assert ctypes.sizeof(_cabi.Problem) == 6 * 4 + 2 * 8 + 8 * 8
     assert _cabi.Problem.scale.offset == 24 and _cabi.Problem.X.offset == 40
 
 

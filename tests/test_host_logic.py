@@ -232,3 +232,31 @@ def test_state_dict_roundtrip(tmp_path):
         LCGP(y=y, x=x, q=3).load_state_dict(a.state_dict())
     with pytest.raises(ValueError):
         LCGP(y=y * 2.0 + 1.0, x=x[::-1].copy(), q=2).load_state_dict(a.state_dict())
+
+
+def test_lbfgsb_machine_equals_scipy_minimize():
+    """lcgp_b200.lbfgsb.LbfgsbMachine (the reverse-communication form the lock-step batched fits advance) visits the
+    points of scipy.optimize.minimize(method='L-BFGS-B') -- the reference's optimizer, lcgp.py:537-540 -- bit for bit,
+    with default options and with an iteration limit."""
+    import scipy.optimize as so
+    from lcgp_b200.lbfgsb import LbfgsbMachine
+
+    def fg(x):
+        return so.rosen(x) + 0.1 * np.sum(np.sin(3 * x)), so.rosen_der(x) + 0.3 * np.cos(3 * x)
+    x0 = np.linspace(-1.2, 1.5, 12)
+    for opts in ({}, {'maxiter': 7}, {'maxcor': 4, 'gtol': 1e-9, 'ftol': 1e-14}):
+        path = []
+
+        def fun(x):
+            path.append(x.copy())
+            return fg(x)
+        r = so.minimize(fun, x0, jac=True, method='L-BFGS-B', options=opts or None)
+        m = LbfgsbMachine(x0, **opts)
+        path2 = []
+        while m.advance():
+            path2.append(m.x.copy())
+            m.supply(*fg(m.x))
+        assert len(path) == len(path2) and all(np.array_equal(a, b) for a, b in zip(path, path2))
+        assert (r.nfev, r.nit, bool(r.success)) == (m.nfev, m.nit, m.success)
+        assert np.array_equal(r.x, m.x) and r.fun == float(m.f)
+    assert not m.advance()                              # stays stopped
