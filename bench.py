@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fit', action='store_true', help='skip the end-to-end fit() wall-time measurement')
+    ap.add_argument('--no-named-configs', action='store_true',
+                    help='skip the evals/s of BASELINE configs 1, 2, 3, 5 at their named shapes (N = 1 only, ~1 min with the CPU port)')
     ap.add_argument('--fit-config', default='cfg3_rep',
                     help="configuration of the fit() wall-time measurement; 'workload' = the bench configuration itself "
                          '(several minutes at config 4 on one GPU); under torchrun (N > 1) the default is the workload, '
@@ -216,6 +218,54 @@ def fit_wall(cfg_name, with_cpu, cpu_s_per_eval=None, sharded=False):
             out['cpu_port_fit_s_extrapolated'] = per_eval * m.n_evals
         except Exception as ex:
             out['cpu_port_s_per_eval'] = f'failed: {ex!r}'
+    return out
+
+
+def named_configs(with_cpu, reps=20):
+    """BASELINE.json configs 1, 2, 3, 5 at their NAMED shapes (config 4 is the bench workload itself): objective +
+    gradient evaluations per second through LCGP.loss_and_grad() (host parameters in, host gradient out), beside one
+    oracle evaluation (torch float64 CPU port, forward + autograd backward) on this box's host cores."""
+    from lcgp_b200 import LCGP, synthetic
+    cases = []
+    x, y, _, _ = synthetic.rep1d_skewed()
+    cases += [('cfg1_rep1d_q2', x, y, dict(q=2, submethod='rep')), ('cfg1_rep1d_q3_notebook', x, y, dict(q=3, submethod='rep'))]
+    x, y, _ = synthetic.rep3d()
+    cases.append(('cfg2_rep3d', x, y, dict(q=3, submethod='rep')))
+    for name in ('cfg3_rep', 'cfg3_full', 'cfg5_one'):
+        x, y, _, _, mk = synthetic.make_config(name)
+        cases.append((name, x, y, mk))
+    out = {}
+    for name, x, y, mk in cases:
+        m = LCGP(y=y, x=x, shard=False, **mk)
+        for _ in range(3):
+            f, g = m.loss_and_grad()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m.loss_and_grad()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        ent = {'n': int(m.n), 'd': int(m.d), 'p': int(m.p), 'q': int(m.q), 'submethod': m.submethod,
+               'ms_per_eval': dt * 1e3, 'evals_per_s': 1.0 / dt, 'objective': f}
+        if with_cpu:
+            try:
+                from oracle.lcgp_oracle import LCGPOracle
+                torch.set_num_threads(os.cpu_count() or 1)
+                o = LCGPOracle(y=y, x=x, skip_xnorm=True, **mk)
+                fn = o.neglpost_chol if mk['submethod'] == 'full' else None
+                o.loss_and_grad(fn)
+                k = 1 if int(m.n) >= 1000 else 5
+                t1 = time.perf_counter()
+                for _ in range(k):
+                    fo, _g = o.loss_and_grad(fn)
+                per = (time.perf_counter() - t1) / k
+                ent.update(cpu_port_s_per_eval=per, cpu_cores=os.cpu_count() or 1, speedup_vs_cpu_port=per / dt,
+                           objective_rel_diff_vs_port=abs(f - fo) / abs(fo))
+            except Exception as ex:
+                ent['cpu_port_s_per_eval'] = f'failed: {ex!r}'
+        out[name] = ent
+        del m
+        torch.cuda.empty_cache()
     return out
 
 
@@ -423,6 +473,8 @@ def run_ours(args):
     if not args.no_fit:
         del model, eng
         torch.cuda.empty_cache()
+        if rank == 0 and world == 1 and not args.no_named_configs:
+            line['named_configs'] = named_configs(not args.no_cpu_baseline)
         cpu_pe = None
         if rank == 0 and fit_cfg == args.config and line.get('cpu_baseline') and line['cpu_baseline'].get('value'):
             cpu_pe = 1.0 / line['cpu_baseline']['value']

@@ -9,5 +9,6 @@ from .model import LCGP  # noqa: F401
 from .kernels import Matern32  # noqa: F401
 from . import evaluation  # noqa: F401
 from .batched import fit_emulators, perturbed_restart  # noqa: F401
+from .harness import LCGPRun, SuperRun  # noqa: F401
 
 __version__ = '0.1.0'

@@ -115,3 +115,6 @@ class OracleEngine:
 
     def aux(self):
         return self._alpha, self._m
+
+    def ainv(self, k):
+        return torch.cholesky_inverse(self._L[k])

@@ -387,6 +387,30 @@ def test_device_preprocessing_equals_host_preprocessing(sub, robust):
     assert abs(fd - fh) <= 1e-13 * abs(fh) and np.max(np.abs(gd - gh)) <= 1e-12 * np.max(np.abs(gh))
 
 
+def test_gram_basis_equals_svd_basis():
+    """Constructor at large p (f-1): phi from the eigen-decomposition of the p x p Gram matrix (device product + host
+    eigh) against phi from the p x n SVD the reference computes (lcgp.py:464-479), columns sign-fixed (SURVEY B-15);
+    diag_D, the objective and its gradient agree to the north-star tolerances."""
+    x, y, x0, _ = synthetic.latent_mixture(n=900, d=4, p=320, q_true=8, seed=77, rep_choices=(1, 2), n0=16)
+    mg = LCGP(y=y, x=x, q=8, submethod='rep', device_preprocess=True)     # p >= 256, 4 q <= p <= n: Gram path
+    ms = LCGP(y=y, x=x, q=8, submethod='rep', device_preprocess=False)    # host SVD
+    calls = []
+    orig = mg._gram_basis
+    mg._gram_basis = lambda Y, q: (calls.append(1), orig(Y, q))[1]
+    mg.init_phi()
+    assert calls, 'the Gram path was not taken'
+    sg = torch.sign(mg.phi[mg.phi.abs().argmax(dim=0), torch.arange(8)])
+    ss = torch.sign(ms.phi[ms.phi.abs().argmax(dim=0), torch.arange(8)])
+    assert rel(mg.phi * sg, ms.phi * ss) < 1e-10
+    assert rel(mg.diag_D, ms.diag_D) < 1e-11
+    fg, gg = mg.loss_and_grad()
+    fs, gs = ms.loss_and_grad()
+    assert abs(fg - fs) <= NLL_TOL * abs(fs) and np.max(np.abs(gg - gs)) <= GRAD_TOL * np.max(np.abs(gs))
+    # ill-separated request (all p components of a rank-deficient matrix): the Gram path declines
+    Yb = torch.randn(300, 5, dtype=DT) @ torch.randn(5, 400, dtype=DT)
+    assert mg._gram_basis(Yb, 20) == (None, None)
+
+
 @pytest.mark.parametrize('m', [1, 2, 7, 256, 1001, 8000])
 def test_row_select_is_the_nearest_rank_percentile(m):
     """lcgp_prep_row_select == sorted row at index round((m-1)/2) (tfp 'nearest' percentile), incl. ties, negative
@@ -553,6 +577,22 @@ def test_notebook_goldens_through_cuda_path():
     assert round(float(cov), 3) == GOLD['coverage'] and round(float(width), 4) == GOLD['width']
     assert abs(evaluation.dss(ytrue, yp, ycv, use_diag=True) - GOLD['dss']) < 2e-4
     assert np.all(ypv > 0) and np.all(ycv <= ypv + 1e-9)         # test_rep.py:203-232
+
+
+def test_example_harness_trains_and_predicts():
+    """LCGPRun.train / predict (docs/call_model.py:59-86) through the CUDA path: numpy outputs, (p, n0) or transposed
+    with as_pxn, 4-tuple with the full covariance in 'full' mode, prediction at the training inputs."""
+    from lcgp_b200 import LCGPRun
+    x, y = make_full_data(seed=5, n=60, p=3, d=2)
+    run = LCGPRun(runno='t', data=dict(xtrain=x, ytrain=y, xtest=x[:7] + 0.01, ytest=y[:, :7]), submethod='full', num_latent=2)
+    run.define_model()
+    run.train()
+    ym, ypv, ycv = run.predict()
+    assert isinstance(ym, np.ndarray) and ym.shape == (3, 7) and (ypv > 0).all() and (ycv <= ypv + 1e-9).all()
+    t = run.predict(as_pxn=True)
+    assert t[0].shape == (7, 3) and np.array_equal(t[0].T, ym)
+    out = run.predict(train=True, return_fullcov=True)
+    assert len(out) == 4 and out[0].shape == (3, 60) and out[3].shape == (60, 3, 3)
 
 
 def test_reference_behaviour_contract():

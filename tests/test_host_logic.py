@@ -213,6 +213,36 @@ def test_evaluation_metrics():                 # test_diagnostics.py
     assert abs(evaluation.dss(y, y + 0.1, full, use_diag=False) - evaluation.dss(y, y + 0.1, np.ones_like(y), True)) < 1e-12
 
 
+def test_dss_full_covariance_matches_its_definition():
+    """evaluation.dss(use_diag=False) (src/lcgp/evaluation.py:21-49: log det Sigma + r^T Sigma^-1 r through an
+    eigen-decomposition, averaged over test points) against a direct solve, for random SPD covariances."""
+    rng = np.random.default_rng(3)
+    p, n = 4, 9
+    y, mu = rng.standard_normal((p, n)), rng.standard_normal((p, n))
+    A = rng.standard_normal((n, p, p))
+    S = np.einsum('nij,nkj->nik', A, A) + 0.5 * np.eye(p)
+    want = np.mean([np.linalg.slogdet(S[i])[1] + (y[:, i] - mu[:, i]) @ np.linalg.solve(S[i], y[:, i] - mu[:, i]) for i in range(n)])
+    assert abs(evaluation.dss(y, mu, np.moveaxis(S, 0, 2), use_diag=False) - want) <= 1e-12 * abs(want)
+    d = rng.uniform(0.5, 2.0, (p, n))                  # diagonal covariances: both forms agree
+    Sd = np.stack([np.diag(d[:, i]) for i in range(n)], axis=2)
+    assert abs(evaluation.dss(y, mu, Sd, use_diag=False) - evaluation.dss(y, mu, d, use_diag=True)) < 1e-12
+
+
+def test_example_harness_interface():
+    """LCGPRun / SuperRun (docs/call_model.py:5-86): constructor keywords, attributes, swallowed extras; the model is
+    built with the harness' settings.  (train / predict need the CUDA path: tests/test_gpu_parity.py.)"""
+    from lcgp_b200 import LCGPRun
+    x, y = make_full_data(n=30, p=3, d=2)
+    data = dict(xtrain=x, ytrain=y, xtest=x[:5], ytest=y[:, :5], ytrue=y[:, :5])
+    run = LCGPRun(runno='r0', data=data, submethod='rep', robust=False, num_latent=2, err_struct=[1, 2],
+                  diag_error_structure=[3], robust_mean=True)                 # the last two are swallowed (SURVEY B-10)
+    assert run.modelname == 'LCGP' and run.n == 30 and run.num_output == 3 and run.model is None and hasattr(run, 'ytrue')
+    assert LCGPRun(runno='r1', data=data).modelname == 'LCGP_robust'
+    run.define_model()
+    m = run.model
+    assert m.submethod == 'rep' and int(m.q) == 2 and m.robust_mean is False and m.diag_error_structure == [1, 2]
+
+
 def test_synthetic_configs_shapes():
     x, y, x0, y0, mk = synthetic.make_config('cfg5_one')
     assert x.shape == (1024, 6) and y.shape == (64, 1024) and mk['q'] == 8

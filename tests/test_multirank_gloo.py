@@ -30,10 +30,11 @@ def _worker(rank, world, port, q, ret):
         x0 = np.random.default_rng(3).uniform(0, 1, (9, 2))
         yp, ypv, ycv = m.predict(x0)
         cinv = m.CinvMs.numpy().copy()
+        tk = m.Tks[q - 1].numpy().copy()       # dense operator of the LAST latent: rebuilt by its owner, broadcast to all
         m.fit(maxiter=5)                      # also invalidates the cached aux quantities
         assert bool(torch.isnan(m.CinvMs).all())
         ret[rank] = dict(local=m._local_idx.tolist(), f=f, g=g, yp=yp.numpy(), ypv=ypv.numpy(),
-                         fitted=m._flat_get(), cinv=cinv)
+                         fitted=m._flat_get(), cinv=cinv, tk=tk)
     finally:
         dist.destroy_process_group()
 
@@ -67,3 +68,6 @@ def test_sharded_objective_gradient_predict_fit(q, world):
     assert np.max(np.abs(r0['yp'] - ypo.numpy())) <= 1e-8 * np.max(np.abs(ypo.numpy()))
     assert np.max(np.abs(r0['ypv'] - ypvo.numpy())) <= 1e-8 * np.max(np.abs(ypvo.numpy()))
     assert np.max(np.abs(r0['cinv'] - o.CinvMs.numpy())) <= 1e-8 * np.max(np.abs(o.CinvMs.numpy()))
+    tko = o.Tks[q - 1].numpy()                  # oracle in the stable form (SURVEY B-4)
+    for rk in range(world):
+        assert np.max(np.abs(ret[rk]['tk'] - tko)) <= 1e-8 * np.max(np.abs(tko))
