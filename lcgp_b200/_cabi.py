@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'liblcgp_b200.so')
+LIB_PATH = os.environ.get('LCGP_B200_LIB') or os.path.join(_HERE, '_lib', 'liblcgp_b200.so')   # (override: A/B builds)
 NB = 128
 MAX_D = 64
 N_STAGE_EVENTS = 7

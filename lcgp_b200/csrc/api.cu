@@ -115,8 +115,8 @@ struct Workspace {
 
 static inline size_t al(size_t x) { return (x + 31) / 32 * 32; }
 // group g (latents [g0, g0 + cnt)) uses the region at sync_off(nb, g, g0) of potrf_pll_sync_ints(nb, cnt) ints
-static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)4 * nb * g0; }
-static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)4 * nb * q; }
+static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)6 * nb * g0; }
+static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)6 * nb * q; }
 
 // q = all latents of the call (E emulators x q / E latents each)
 static Workspace layout(int n, int d, int p, int q, int E, void* basep) {

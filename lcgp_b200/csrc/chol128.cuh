@@ -41,7 +41,133 @@ constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;   // 189,056 B
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// ---- Panel factorisation of sub-block column s by the whole CTA (256 threads) ------------------------------------
+// ---- Panel factorisation of sub-block column S by the whole CTA (256 threads) ------------------------------------
+// The tall panel  [ S(s,s) ; S(s+1..3, s) ; I_32 ]  (NR = 160 - 32 s rows x 32 columns) is eliminated column by column
+// (right-looking, unscaled "LDL^T in flight" form: a_ij -= u_i u_j / d, the square roots are applied at the end).
+// Rows below the diagonal sub-block come out as X = A L_ss^-T, the identity rows as L_ss^-T = W_ss^T -- so the
+// panel solve and the inverse of the diagonal sub-block cost no separate pass.
+// Thread (rg = tid / TXP, tx = tid % TXP) owns ROWS rows rho = rg + (256 / TXP) m and 32 / TXP columns j = tx + TXP n,
+// with (ROWS, TXP) = (5, 8), (2, 4), (3, 8), (1, 4) for s = 0..3: every thread owns exactly NR * 32 / 256 elements, so
+// no FP64 issue slot is spent on padding (a warp can issue a DFMA only every ~6 cycles: the issue slots, not the
+// dependent chain, bound this phase; the first version, 3 rows x 8 columns for every s, took the same 10.5 k cycles
+// for 64 rows as for 160).  Column c is published through shared memory (double buffered), ONE CTA barrier per
+// column; the owners of column c + 1 update and publish it before the rest of the rank-1 update.
+// Dependent chain per column:  LDS -> reciprocal (47 cycles) -> multiply -> FMA -> STS -> barrier.
+constexpr int CBP = 160;                // doubles per column buffer
+__device__ __forceinline__ void bar_cta() { __syncthreads(); }
+
+template <int S>
+__device__ __forceinline__ void panel32(double* __restrict__ sm) {
+    constexpr int NBELOW = (3 - S) * SB;            // rows below the diagonal sub-block
+    constexpr int NR = 2 * SB + NBELOW;             // + diagonal sub-block + identity rows
+    constexpr int TXP = (S & 1) ? 4 : 8;            // column phases
+    constexpr int LOGT = (S & 1) ? 2 : 3;
+    constexpr int RG = 256 / TXP;                   // row groups
+    constexpr int ROWS = NR / RG;                   // 5, 2, 3, 1
+    constexpr int COLS = SB / TXP;                  // 4, 8, 4, 8
+    static_assert(ROWS * RG == NR, "rows must divide evenly");
+    double* Sb = sm + OFF_S;
+    double* W = sm + OFF_W;
+    double* pivs = sm + OFF_PIV + S * SB;
+    double* invd = sm + OFF_INVD + S * SB;
+    double* colbuf = sm + OFF_COL;
+    const int tid = threadIdx.x, rg = tid / TXP, tx = tid % TXP;
+    double a[ROWS][COLS];
+    double* rowp[ROWS];                             // shared-memory row of a data row (null: identity row)
+    int rho[ROWS];
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) {
+        rho[m] = rg + RG * m;
+        rowp[m] = nullptr;
+        if (rho[m] < SB) rowp[m] = Sb + tri(S, S) * BLK + rho[m] * BP;
+        else if (rho[m] < SB + NBELOW) rowp[m] = Sb + tri(S + 1 + ((rho[m] - SB) >> 5), S) * BLK + ((rho[m] - SB) & 31) * BP;
+#pragma unroll
+        for (int n = 0; n < COLS; ++n) {
+            const int j = tx + TXP * n;
+            a[m][n] = rowp[m] ? rowp[m][j] : ((rho[m] - SB - NBELOW == j) ? 1.0 : 0.0);
+        }
+    }
+    if (tx == 0) {                                  // publish column 0
+#pragma unroll
+        for (int m = 0; m < ROWS; ++m) colbuf[rho[m]] = a[m][0];
+    }
+    bar_cta();
+    // software pipelined by one column: the loads and the reciprocal of column c + 1 are issued before the bulk of
+    // column c's rank-1 update
+    double d = colbuf[0];
+    double tt[ROWS], u[COLS];
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) tt[m] = colbuf[rho[m]];
+#pragma unroll
+    for (int n = 0; n < COLS; ++n) u[n] = colbuf[tx + TXP * n];
+    double rd = fast_rcp(d);
+#pragma unroll
+    for (int c = 0; c < SB; ++c) {
+        double* nb_ = colbuf + ((c + 1) & 1) * CBP;
+        const int n0 = c >> LOGT;                   // column groups n < n0 are finished; n == n0 is active iff tx > c % TXP
+        const int n1 = (c + 1) >> LOGT;             // group of column c + 1
+        double t[ROWS];
+#pragma unroll
+        for (int m = 0; m < ROWS; ++m) t[m] = tt[m] * rd;
+        if (tid == 0) pivs[c] = d;
+        if (c + 1 < SB) {                           // column c + 1 first; its owners publish it at once
+            if ((n1 > n0) || (tx > (c & (TXP - 1)))) {
+#pragma unroll
+                for (int m = 0; m < ROWS; ++m) a[m][n1] = fma(-t[m], u[n1], a[m][n1]);
+            }
+            if (tx == ((c + 1) & (TXP - 1))) {
+#pragma unroll
+                for (int m = 0; m < ROWS; ++m) nb_[rho[m]] = a[m][n1];
+            }
+        }
+        bar_cta();
+        double ucur[COLS];
+#pragma unroll
+        for (int n = 0; n < COLS; ++n) ucur[n] = u[n];
+        if (c + 1 < SB) {                           // next column: loads and reciprocal, ahead of this column's bulk
+            d = nb_[c + 1];
+#pragma unroll
+            for (int m = 0; m < ROWS; ++m) tt[m] = nb_[rho[m]];
+#pragma unroll
+            for (int n = n1; n < COLS; ++n) u[n] = nb_[tx + TXP * n];
+            rd = fast_rcp(d);
+        }
+#pragma unroll
+        for (int n = n0; n < COLS; ++n) {           // the rest of the rank-1 update (registers only)
+            if (n == n1 && c + 1 < SB) continue;
+            if ((n > n0) || (tx > (c & (TXP - 1)))) {
+#pragma unroll
+                for (int m = 0; m < ROWS; ++m) a[m][n] = fma(-t[m], ucur[n], a[m][n]);
+            }
+        }
+    }
+    // 1 / L_cc = rsqrt(d_c), once per column
+    if (tid < SB) invd[tid] = rsqrt(pivs[tid]);
+    bar_cta();
+    double* Wd = W + tri(S, S) * BLK;
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) {
+#pragma unroll
+        for (int n = 0; n < COLS; ++n) {
+            const int j = tx + TXP * n;
+            const double v = a[m][n] * invd[j];
+            if (rho[m] < SB) rowp[m][j] = (j <= rho[m]) ? v : 0.0;              // L_ss (zeros above the diagonal)
+            else if (rowp[m]) rowp[m][j] = v;                                    // X = A L_ss^-T
+            else {                                                               // identity row i: W_ss[j][i]
+                const int i = rho[m] - SB - NBELOW;
+                Wd[j * BP + i] = (j >= i) ? v : 0.0;
+            }
+        }
+    }
+}
+
+// ---- The same panel factorisation in COMPACT form: one instantiation (3 rows x 8 columns per thread, rows beyond the
+// panel predicated) for every s.  It wastes FP64 issue slots (10.5 k cycles per step whatever s) but its code is a
+// quarter of the size of the four panel32<S> instantiations.  That matters inside the persistent Cholesky kernel when
+// the factor buffers do not fit in L2: the diagonal-block code runs once in a while per SM, is evicted from L2 by the
+// operand streams in between, and is then re-fetched line by line (measured, same kernel otherwise: 2048 x 10
+// matrices 1.60 ms compact vs 1.72 ms specialised; 1024 x 1 0.53 vs 0.50 ms).
+
 // The tall panel  [ S(s,s) ; S(s+1..3, s) ; I_32 ]  (160 - 32 s rows x 32 columns) is eliminated column by column
 // (right-looking, unscaled "LDL^T in flight" form: a_ij -= u_i u_j / d, the square roots are applied at the end).
 // Rows below the diagonal sub-block come out as X = A L_ss^-T, the identity rows as L_ss^-T = W_ss^T -- so the
@@ -52,14 +178,12 @@ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // ONE CTA barrier per column; the owners of column c + 1 update and publish it before their other updates.
 // Dependent chain per column:  LDS -> reciprocal -> multiply -> FMA -> STS -> barrier (~130 cycles); measured ~300 per
 // column including the rank-1 FMAs (a warp issues one DFMA per ~6 cycles; 21 per thread and column at most).
-constexpr int CBP = 160;                // doubles per column buffer
-__device__ __forceinline__ void bar_cta() { __syncthreads(); }
 
 // The 32 column steps for a thread that owns mr <= MR rows (rho[0..mr)) x 8 columns (tx + 4 n).  ONE instantiation for
 // the whole CTA: per-warp instantiations by row count (fewer wasted FMAs) were measured and gave wrong results --
 // barriers reached from different code copies did not order the column buffers -- for a 15 % gain at best.
 template <int MR>
-__device__ __forceinline__ void panel32_cols(double (&a)[3][8], const int (&rho)[3], int tx, double* __restrict__ colbuf,
+__device__ __forceinline__ void panel32c_cols(double (&a)[3][8], const int (&rho)[3], int tx, double* __restrict__ colbuf,
                                              double* __restrict__ pivs, int mr) {
 #pragma unroll
     for (int c = 0; c < SB; ++c) {
@@ -101,7 +225,7 @@ __device__ __forceinline__ void panel32_cols(double (&a)[3][8], const int (&rho)
     }
 }
 
-__device__ __forceinline__ void panel32(double* __restrict__ sm, int s) {
+__device__ __forceinline__ void panel32_compact(double* __restrict__ sm, int s) {
     double* S = sm + OFF_S;
     double* W = sm + OFF_W;
     double* pivs = sm + OFF_PIV + s * SB;
@@ -133,7 +257,7 @@ __device__ __forceinline__ void panel32(double* __restrict__ sm, int s) {
             if (m < mr) colbuf[rho[m]] = a[m][0];
     }
     bar_cta();
-    panel32_cols<3>(a, rho, tx, colbuf, pivs, mr);
+    panel32c_cols<3>(a, rho, tx, colbuf, pivs, mr);
     // 1 / L_cc = rsqrt(d_c), once per column
     if (tid < SB) invd[tid] = rsqrt(pivs[tid]);
     bar_cta();
@@ -203,8 +327,9 @@ __device__ __forceinline__ void store_unit(double* __restrict__ C, const double 
 // On return: S blocks (i > j) and the lower triangles of S(i,i) hold L -- but the diagonal S blocks are CLOBBERED by
 // the inverse phase, so `write_L` is invoked (by all threads, after a barrier) between the two phases to save L;
 // W blocks hold inv(L) (lower triangular, zeros above the diagonal of the diagonal sub-blocks); pivs / invd filled.
+// compact: use panel32_compact (small code) instead of the per-step specialisations
 template <class WriteL>
-__device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL write_L) {
+__device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL write_L, bool compact = false) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     double* S = sm + OFF_S;
@@ -214,7 +339,13 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
     for (int s = 0; s < 4; ++s) {
         C128_STAMP(4 * s + 0);
         // ---- P1 + P2: panel factorisation (diagonal sub-block, rows below, inverse of the sub-block)
-        panel32(sm, s);
+        if (compact) panel32_compact(sm, s);
+        else switch (s) {                                            // (ROWS, TXP) differ per step: see panel32
+            case 0: panel32<0>(sm); break;
+            case 1: panel32<1>(sm); break;
+            case 2: panel32<2>(sm); break;
+            default: panel32<3>(sm); break;
+        }
         __syncthreads();
         C128_STAMP(4 * s + 1);
         C128_STAMP(4 * s + 2);
@@ -285,23 +416,24 @@ __device__ __forceinline__ void factor_invert(double* __restrict__ sm, WriteL wr
 // ---- global <-> shared ----------------------------------------------------------------------------------
 // Loads rows [r0, r0 + NR) of the lower triangle of the 128 x 128 block at blk (row-major, ld) into the S sub-blocks
 // (zeros above the diagonal of the diagonal sub-blocks).  L2 loads (the block may have been written by another SM of
-// the same kernel); 16 loads per thread are in flight before the first is consumed.  NR = 128 or 64.
+// the same kernel); up to 16 loads per thread are in flight before the first is consumed.  NR = 128, 64 or 32.
 template <int NR>
 __device__ __forceinline__ void load_rows(double* __restrict__ sm, const double* __restrict__ blk, size_t ld, int r0) {
     double* S = sm + OFF_S;
     constexpr int PAIRS = NR * (NB / 2);
-    static_assert(PAIRS % (256 * 16) == 0, "load_rows assumes 256 threads");
+    constexpr int U = PAIRS / 256 < 16 ? PAIRS / 256 : 16;      // loads in flight per thread
+    static_assert(PAIRS % (256 * U) == 0, "load_rows assumes 256 threads");
 #pragma unroll 1
-    for (int base = 0; base < PAIRS; base += 256 * 16) {
-        double2 v[16];
+    for (int base = 0; base < PAIRS; base += 256 * U) {
+        double2 v[U];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int idx = base + u * 256 + threadIdx.x;
             const int r = r0 + (idx >> 6), c = (idx & 63) * 2;
             v[u] = (c <= r) ? __ldcg(reinterpret_cast<const double2*>(blk + (size_t)r * ld + c)) : make_double2(0.0, 0.0);
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int idx = base + u * 256 + threadIdx.x;
             const int r = r0 + (idx >> 6), c = (idx & 63) * 2;
             if ((c >> 5) <= (r >> 5)) {             // sub-block on or below the diagonal (zeros above the diagonal inside it)

@@ -42,6 +42,7 @@ struct GemmMaps {                         // TMA view: 3-D maps (column, row, ba
     CUtensorMap km[NSRC];                 // box 16 x 128 x 1  (K-major operand: 16 k-columns of 128 rows)
     CUtensorMap nm[2];                    // box 16 x 32 x 1   (N-major operand from SRC_F / SRC_DU)
     CUtensorMap km64;                     // box 16 x 64 x 1   (operand A of half-tile launches, from SRC_F)
+    CUtensorMap km32;                     // box 16 x 32 x 1   (operand A of quarter-tile tasks of the persistent Cholesky)
 };
 
 // Storage convention for one latent's factor buffer F (np x np, row-major, np % NB == 0):

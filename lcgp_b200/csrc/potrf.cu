@@ -122,6 +122,8 @@ cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSR
         if (i == SRC_F) {   // half-tile launches: operand A boxes of 64 rows
             e = encode_map(&ctx.maps.km64, srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB / 2);
             if (e != cudaSuccess) return e;
+            e = encode_map(&ctx.maps.km32, srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB / 4);
+            if (e != cudaSuccess) return e;
         }
     }
     return cudaSuccess;

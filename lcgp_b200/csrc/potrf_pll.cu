@@ -37,10 +37,11 @@ struct PllParams {
     double* logdet_part;   // [batch][nb] or null
     int* info;             // [batch]
     int* hdr;              // [0] ticket counter, [1] spare
-    int* rowdone;          // [batch][nb][2]
+    int* rowdone;          // [batch][nb][4]
     int* diagdone;         // [batch][nb]
     int* diagcnt;          // [batch][nb]
     int ntasks;
+    int compact_diag;      // 1: small-code diagonal-block panels (factor buffers larger than L2), see chol128.cuh
     long long timeout;     // cycles
 };
 
@@ -73,6 +74,40 @@ __device__ __forceinline__ int wait_flag_ge(const int* p, int target, const PllP
     }
 }
 
+// The diagonal block: rows [h * mt, (h + 1) * mt) are already in shared memory (the caller put them there from its
+// accumulators), the other row slices come back from L2.  Factor, invert, hand DL over (flag), then write the rest.
+// NOT inlined: the panel code (chol128.cuh) is large and register hungry; inlined into the persistent kernel it
+// degraded the register allocation of the hot K loop (64-row tasks ran 7-9 % slower).
+__device__ __noinline__ void pll_diag_block(double* dsm, double* blk, int np, double* dl, double* du, int* done_flag,
+                                            int* info, double* logdet_slot, int j, int h, int mt, bool compact) {
+    const int tid = threadIdx.x;
+    if (mt == NB / 2) c128::load_rows<NB / 2>(dsm, blk, np, (1 - h) * (NB / 2));
+    else if (mt == NB / 4) {
+#pragma unroll 1
+        for (int hh = 0; hh < 4; ++hh)
+            if (hh != h) c128::load_rows<NB / 4>(dsm, blk, np, hh * (NB / 4));
+    }
+    __syncthreads();
+    // the diagonal sub-blocks of L are scratch of the inverse phase: they go to global before it, the rest of L
+    // and DU after DL has been handed over
+    c128::factor_invert(dsm, [&] { c128::store_L_part<true>(dsm, blk, np); }, compact);
+    c128::store_DL(dsm, dl);
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag), "r"(1) : "memory");   // the solves of column j may start
+    c128::store_L_part<false>(dsm, blk, np);
+    c128::store_DU(dsm, du);
+    const double* pivs = dsm + c128::OFF_PIV;
+    if (tid == 0) {
+        for (int c = 0; c < NB; ++c)
+            if (!(pivs[c] > 0.0)) { atomicCAS(info, 0, j * NB + c + 1); break; }
+    }
+    double lg = (tid < NB) ? 0.5 * log(pivs[tid]) : 0.0;
+    lg = block_sum(lg, dsm + c128::OFF_RED);
+    if (tid == 0 && logdet_slot) *logdet_slot = lg;
+}
+
 constexpr int PLL_DATA_BYTES = STAGES * (NB * BK * 8 + TMA_B_BYTES);     // 192 KB: ring / TRSM staging / diagonal block
 constexpr int PLL_NBAR = 2 * STAGES + 4;
 constexpr size_t PLL_SMEM = (size_t)PLL_DATA_BYTES + 8 * PLL_NBAR + 64 + 1024;
@@ -81,7 +116,7 @@ static_assert(c128::SMEM_BYTES <= (size_t)PLL_DATA_BYTES, "diagonal-block routin
 template <int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ GemmMaps maps) {
-    constexpr int H = NB / MT;                       // halves per tile
+    constexpr int H = NB / MT;                       // row slices per tile (1, 2 or 4)
     constexpr int MI = MT / 16;
     constexpr int ABYTES = MT * BK * 8;              // operand A per K stage
     constexpr int STAGE_BYTES = ABYTES + TMA_B_BYTES;
@@ -102,7 +137,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
 #pragma unroll
         for (int s = 0; s < 4; ++s) mbar_init(dlbar0 + 8 * s, 1);
         mbar_fence_init();
-        tma_prefetch_desc(MT == NB ? &maps.km[SRC_F] : &maps.km64);
+        tma_prefetch_desc(MT == NB ? &maps.km[SRC_F] : (MT == NB / 2 ? &maps.km64 : &maps.km32));
         tma_prefetch_desc(&maps.km[SRC_F]);
         tma_prefetch_desc(&maps.km[SRC_DL]);
     }
@@ -132,8 +167,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         const int moff = h * MT;
         double* Fb = P.v.F + (size_t)b * P.v.fstride;
         double* Ct = Fb + ((size_t)i * NB + moff) * np + (size_t)j * NB;       // this task's rows of tile (i, j)
-        const int* rd_i = P.rowdone + ((size_t)b * nb + i) * 2 + h;
-        const int* rd_j = P.rowdone + ((size_t)b * nb + j) * 2;
+        const int* rd_i = P.rowdone + ((size_t)b * nb + i) * 4 + h;
+        const int* rd_j = P.rowdone + ((size_t)b * nb + j) * 4;
 
         // ---- acc = -A(i,j): the tile loads overlap the pipeline fill
         double acc[MI][4][2];
@@ -163,7 +198,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                     if (seen_i <= k) seen_i = wait_flag_ge(rd_i, k + 1, P, b, 1000 + j);
                     if (seen_j <= k) {
                         int v = wait_flag_ge(rd_j, k + 1, P, b, 2000 + j);
-                        if (H == 2) v = min(v, wait_flag_ge(rd_j + 1, k + 1, P, b, 3000 + j));
+#pragma unroll
+                        for (int hh = 1; hh < H; ++hh) v = min(v, wait_flag_ge(rd_j + hh, k + 1, P, b, 3000 + j));
                         seen_j = v;
                     }
                     fence_proxy_async();
@@ -171,7 +207,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 const unsigned fb = full0 + 8 * slot;
                 mbar_arrive_expect_tx(fb, STAGE_BYTES);
                 const unsigned dA = sm_u + slot * STAGE_BYTES, dB = dA + ABYTES;
-                const CUtensorMap* ma = (MT == NB) ? &maps.km[SRC_F] : &maps.km64;
+                const CUtensorMap* ma = (MT == NB) ? &maps.km[SRC_F] : (MT == NB / 2 ? &maps.km64 : &maps.km32);
 #pragma unroll
                 for (int hh = 0; hh < BK / TMA_BOX_K; ++hh)
                     tma_load_3d(dA + hh * (MT * 128), ma, k * NB + ks * BK + hh * TMA_BOX_K, i * NB + moff, b, fb);
@@ -224,26 +260,10 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                     for (int ni = 0; ni < 4; ++ni)
                         c128::put_pair(dsm, moff + rl, wc.wn * 32 + ni * 8 + 2 * wc.t, -acc[mi][ni][0], -acc[mi][ni][1]);
                 }
-                if (H == 2) c128::load_rows<NB / 2>(dsm, blk, np, (1 - h) * (NB / 2));
-                __syncthreads();
-                // the diagonal sub-blocks of L are scratch of the inverse phase: they go to global before it, the rest of L
-                // and DU after DL has been handed over
-                c128::factor_invert(dsm, [&] { c128::store_L_part<true>(dsm, blk, np); });
-                c128::store_DL(dsm, P.DLw + (size_t)b * P.v.dstride + (size_t)j * NB * NB);
-                __threadfence();
-                fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) st_release_gpu(&P.diagdone[(size_t)b * nb + j], 1);   // the solves of column j may start
-                c128::store_L_part<false>(dsm, blk, np);
-                c128::store_DU(dsm, P.DUw + (size_t)b * P.v.dstride + (size_t)j * NB * NB);
-                const double* pivs = dsm + c128::OFF_PIV;
-                if (tid == 0) {
-                    for (int c = 0; c < NB; ++c)
-                        if (!(pivs[c] > 0.0)) { atomicCAS(&P.info[b], 0, j * NB + c + 1); break; }
-                }
-                double lg = (tid < NB) ? 0.5 * log(pivs[tid]) : 0.0;
-                lg = block_sum(lg, dsm + c128::OFF_RED);
-                if (tid == 0 && P.logdet_part) P.logdet_part[(size_t)b * nb + j] = lg;
+                pll_diag_block(dsm, blk, np, P.DLw + (size_t)b * P.v.dstride + (size_t)j * NB * NB,
+                               P.DUw + (size_t)b * P.v.dstride + (size_t)j * NB * NB, &P.diagdone[(size_t)b * nb + j],
+                               &P.info[b], P.logdet_part ? &P.logdet_part[(size_t)b * nb + j] : nullptr, j, h, MT,
+                               P.compact_diag != 0);
             }
         } else {
             // ---- off-diagonal tile: P = C inv(L_jj)^T.  C goes to shared memory in the layout of a K-major operand-A
@@ -312,10 +332,12 @@ static int env_i(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return (e && *e) ? std::atoi(e) : dflt;
 }
-// LCGP_PLL_HALF: 64-row tasks when nb * batch is at most this (few tiles: latency matters more than operand reuse)
+// LCGP_PLL_HALF / LCGP_PLL_QUARTER: 64-row / 32-row tasks when nb * batch is at most this (few tiles: the latency of the
+// tiles on the dependency chain matters more than operand reuse)
 static int pll_half_limit() { static const int v = env_i("LCGP_PLL_HALF", 160); return v; }
+static int pll_quarter_limit() { static const int v = env_i("LCGP_PLL_QUARTER", 64); return v; }
 
-size_t potrf_pll_sync_ints(int nb, int batch) { return 8 + (size_t)4 * batch * nb; }
+size_t potrf_pll_sync_ints(int nb, int batch) { return 8 + (size_t)6 * batch * nb; }
 
 cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part, int* info,
                       int* sync, cudaStream_t stream) {
@@ -328,6 +350,8 @@ cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, 
         cudaError_t e = cudaFuncSetAttribute(potrf_pll_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PLL_SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_pll_kernel<NB / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PLL_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_pll_kernel<NB / 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PLL_SMEM);
         if (e != cudaSuccess) return e;
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -348,19 +372,27 @@ cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, 
     const size_t nints = potrf_pll_sync_ints(v.nb, batch);
     cudaError_t e = cudaMemsetAsync(sync, 0, nints * sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    const bool half = v.nb * batch <= pll_half_limit();
-    const int H = half ? 2 : 1;
+    // quarter tiles only for small matrices (measured: 1024 x 1 500 -> 450 us, 1024 x 8 533 -> 508, 2048 x 1 1016 -> 914; but
+    // 8064 x 1 7.0 -> 8.4 ms: with many block columns the bulk efficiency of the wider tiles wins)
+    const bool quarter = v.nb <= 16 && v.nb * batch <= pll_quarter_limit();
+    const bool half = !quarter && v.nb * batch <= pll_half_limit();
+    const int H = quarter ? 4 : (half ? 2 : 1);
     PllParams P;
     P.v = v; P.DLw = DLw; P.DUw = DUw; P.batch = batch; P.logdet_part = logdet_part; P.info = info;
     P.hdr = sync;
     P.rowdone = sync + 8;
-    P.diagdone = P.rowdone + (size_t)2 * batch * v.nb;
+    P.diagdone = P.rowdone + (size_t)4 * batch * v.nb;
     P.diagcnt = P.diagdone + (size_t)batch * v.nb;
     P.ntasks = v.nb * (v.nb + 1) / 2 * H * batch;
     P.timeout = (long long)env_i("LCGP_PLL_TIMEOUT_MS", 4000) * 2000000LL;   // ~2 GHz
+    {   // LCGP_PLL_COMPACT: 0 / 1 force; default: compact code once the factor buffers exceed ~half of the 126 MB L2
+        const int f = env_i("LCGP_PLL_COMPACT", -1);
+        P.compact_diag = f >= 0 ? f : ((size_t)batch * v.fstride * sizeof(double) > ((size_t)64 << 20) ? 1 : 0);
+    }
     const int grid = P.ntasks < sms[dev] ? P.ntasks : sms[dev];
     note_launch();
-    if (half) potrf_pll_kernel<NB / 2><<<grid, GEMM_THREADS, PLL_SMEM, stream>>>(P, ctx.maps);
+    if (quarter) potrf_pll_kernel<NB / 4><<<grid, GEMM_THREADS, PLL_SMEM, stream>>>(P, ctx.maps);
+    else if (half) potrf_pll_kernel<NB / 2><<<grid, GEMM_THREADS, PLL_SMEM, stream>>>(P, ctx.maps);
     else potrf_pll_kernel<NB><<<grid, GEMM_THREADS, PLL_SMEM, stream>>>(P, ctx.maps);
     return cudaGetLastError();
 }
