@@ -223,6 +223,13 @@ size_t lcgp_potrf_scratch_bytes(int32_t np, int32_t batch);
 int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
                        int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Cholesky AND triangular inverse in ONE persistent launch (what lcgp_nll_grad runs): as lcgp_potrf_batched with
+ * scratch, and on return the strictly-upper NB-blocks of F also hold L^{-T} (what lcgp_trtri_batched computes).  The
+ * inverse tiles are queued one block column behind the factorisation and fill the SMs its dependency chain leaves
+ * idle.  (tf.linalg.cholesky + the identity solves / tf.linalg.inv of lcgp.py:775-787.) */
+int lcgp_potrf_trtri_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
+                             int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Blocked triangular inverse: fills the strictly-upper NB-blocks of F with L^{-T}.
  * scratch: lcgp_trtri_scratch_bytes(np, batch). */
 size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch);

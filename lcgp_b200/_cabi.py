@@ -57,6 +57,7 @@ _SIGS = {
     'lcgp_build_A': (C.c_int, [_dp, _dp, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp]),
     'lcgp_potrf_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'lcgp_potrf_batched': (C.c_int, [_dp, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp]),
+    'lcgp_potrf_trtri_batched': (C.c_int, [_dp, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_size_t, _dp]),
     'lcgp_trtri_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'lcgp_trtri_batched': (C.c_int, [_dp, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_size_t, _dp]),
 }

@@ -115,8 +115,8 @@ struct Workspace {
 
 static inline size_t al(size_t x) { return (x + 31) / 32 * 32; }
 // group g (latents [g0, g0 + cnt)) uses the region at sync_off(nb, g, g0) of potrf_pll_sync_ints(nb, cnt) ints
-static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)6 * nb * g0; }
-static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)6 * nb * q; }
+static inline size_t sync_off(int nb, int g, int g0) { return (size_t)8 * g + (size_t)10 * nb * g0; }
+static inline size_t sync_ints(int nb, int q) { return (size_t)8 * MAX_GROUPS + (size_t)10 * nb * q; }
 
 // q = all latents of the call (E emulators x q / E latents each)
 static Workspace layout(int n, int d, int p, int q, int E, void* basep) {
@@ -382,6 +382,7 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     // Look-ahead uses the library's shared high-priority streams: skipped when the caller asked for "everything on
     // my stream" (bits 4-7 == 1: many small emulators driven from several host threads would falsely serialise on
     // them) and for small matrices, where no trailing update is big enough to hide a panel behind.
+    const bool fuse = pll && potrf_fuse_trtri();    // triangular inverse inside the persistent Cholesky kernel
     const bool look = !pll && lookahead_on() && !(flags & LCGP_FLAG_NO_LOOKAHEAD) && ((flags >> 4) & 15) != 1 &&
                       w.nb > 16;
     auto potrf_group = [&](int g0, int cnt, cudaStream_t s, int g) {
@@ -392,9 +393,10 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
         }
         return potrf_batched(sub_view(v, g0), w.DL + (size_t)g0 * w.dstride, w.DU + (size_t)g0 * w.dstride, cnt,
                              w.logdet_part + (size_t)g0 * w.nb, info + g0, panel_width(), s, la,
-                             pll ? w.sync + sync_off(w.nb, g, g0) : nullptr);
+                             pll ? w.sync + sync_off(w.nb, g, g0) : nullptr, fuse);
     };
     auto trtri_group = [&](int g0, int cnt, cudaStream_t s, int) {
+        if (fuse) return cudaSuccess;               // done by the persistent Cholesky launch
         return trtri_batched(sub_view(v, g0), w.T + (size_t)g0 * w.tstride, w.tstride, cnt, s);
     };
     if (ev) {
@@ -782,6 +784,20 @@ int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double*
         }
         return potrf_batched(v, DL, DU, batch, logdet_part, info, panel_width(), s, la);
     }));
+}
+
+int lcgp_potrf_trtri_batched(double* F, int32_t np, int32_t batch, double* DL, double* DU, double* logdet_part,
+                             int32_t* info, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!F || !DL || !DU || !info || !scratch || np <= 0 || batch <= 0) return LCGP_E_ARG;
+    if (np % NB != 0) return LCGP_E_DIM;
+    if (scratch_bytes < lcgp_potrf_scratch_bytes(np, batch)) return LCGP_E_WORKSPACE;
+    if (!potrf_use_pll()) return LCGP_E_ARG;        // the fused form exists for the persistent kernel only
+    FactorView v;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
+    cudaStream_t st = (cudaStream_t)stream;
+    LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+    return cuda_rc(potrf_pll(v, DL, DU, batch, logdet_part, info, (int*)scratch, st, true));
 }
 
 size_t lcgp_trtri_scratch_bytes(int32_t np, int32_t batch) {

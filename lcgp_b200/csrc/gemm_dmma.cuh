@@ -43,6 +43,7 @@ struct GemmMaps {                         // TMA view: 3-D maps (column, row, ba
     CUtensorMap nm[2];                    // box 16 x 32 x 1   (N-major operand from SRC_F / SRC_DU)
     CUtensorMap km64;                     // box 16 x 64 x 1   (operand A of half-tile launches, from SRC_F)
     CUtensorMap km32;                     // box 16 x 32 x 1   (operand A of quarter-tile tasks of the persistent Cholesky)
+    CUtensorMap du64, du32;               // the same two box shapes over SRC_DU (fused triangular inverse)
 };
 
 // Storage convention for one latent's factor buffer F (np x np, row-major, np % NB == 0):

@@ -20,13 +20,16 @@ struct Lookahead {
 // of potrf_pll.cu (one launch per call) unless LCGP_POTRF=panels; otherwise the launch-per-block-column path below.
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
                           int* info, int panel_width, cudaStream_t stream, const Lookahead& la = Lookahead(),
-                          int* sync = nullptr);
+                          int* sync = nullptr, bool fused_inverse = false);
+// LCGP_FUSE_TRTRI (default 1): with the persistent kernel the triangular inverse is computed by the same launch
+bool potrf_fuse_trtri();
 bool potrf_use_pll();                     // the persistent kernel is enabled at all (LCGP_POTRF != panels, TMA engine)
 bool potrf_use_pll(int nb, int batch);    // ... and selected for this batch of matrices
 // potrf_pll.cu
 size_t potrf_pll_sync_ints(int nb, int batch);
+// fused_inverse: the same launch also fills the strictly-upper blocks with U = L^-T (what trtri_batched computes)
 cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part, int* info,
-                      int* sync, cudaStream_t stream);
+                      int* sync, cudaStream_t stream, bool fused_inverse = false);
 size_t trtri_scratch_blocks(int nb);
 void factor_srcs(const FactorView& v, GemmSrcs& s, int rows[]);
 cudaError_t trtri_batched(const FactorView& v, double* scratch, size_t tstride, int batch, cudaStream_t stream);

@@ -53,6 +53,13 @@ static int potrf_mode() {   // 0 = auto, 1 = pll, 2 = panels
     return v;
 }
 bool potrf_use_pll() { return potrf_mode() != 2 && gemm_use_tma(); }
+bool potrf_fuse_trtri() {
+    static const bool v = [] {
+        const char* e = std::getenv("LCGP_FUSE_TRTRI");
+        return !(e && std::strcmp(e, "0") == 0);
+    }();
+    return v;
+}
 bool potrf_use_pll(int nb, int batch) {
     if (!potrf_use_pll()) return false;
     return potrf_mode() == 1 || !(batch >= 16 && nb >= 32);
@@ -117,6 +124,12 @@ cudaError_t gemm_make_ctx(GemmCtx& ctx, const GemmSrcs& srcs, const int rows[NSR
         if (i == SRC_F || i == SRC_DU) {
             e = encode_map(&ctx.maps.nm[i == SRC_F ? 0 : 1], srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i],
                            srcs.bstride[i], BK);
+            if (e != cudaSuccess) return e;
+        }
+        if (i == SRC_DU) {
+            e = encode_map(&ctx.maps.du64, srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB / 2);
+            if (e != cudaSuccess) return e;
+            e = encode_map(&ctx.maps.du32, srcs.base[i], srcs.ld[i], rows[i], batch, srcs.ld[i], srcs.bstride[i], NB / 4);
             if (e != cudaSuccess) return e;
         }
         if (i == SRC_F) {   // half-tile launches: operand A boxes of 64 rows
@@ -356,8 +369,9 @@ static cudaError_t diag_configure() {
 //     bulk :            wait factor k  | update_k(cols right of panel k+1) | ...
 // Events are re-recorded every panel (a wait refers to the record that precedes it in host order).
 cudaError_t potrf_batched(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part,
-                          int* info, int pw, cudaStream_t stream, const Lookahead& la, int* sync) {
-    if (sync && potrf_use_pll()) return potrf_pll(v, DLw, DUw, batch, logdet_part, info, sync, stream);   // callers apply the size rule
+                          int* info, int pw, cudaStream_t stream, const Lookahead& la, int* sync, bool fused_inverse) {
+    if (sync && potrf_use_pll()) return potrf_pll(v, DLw, DUw, batch, logdet_part, info, sync, stream, fused_inverse);   // callers apply the size rule
+    if (fused_inverse) return cudaErrorNotSupported;
     cudaError_t e = diag_configure();
     if (e != cudaSuccess) return e;
     if (pw < 1) pw = batch >= 8 ? 16 : 8;   // auto: wide panels pay once the batch alone fills the SMs

@@ -38,8 +38,10 @@ struct PllParams {
     int* info;             // [batch]
     int* hdr;              // [0] ticket counter, [1] spare
     int* rowdone;          // [batch][nb][4]
-    int* diagdone;         // [batch][nb]
+    int* diagdone;         // [batch][nb]: 1 = L_jj and DL_jj published, 2 = DU_jj as well
     int* diagcnt;          // [batch][nb]
+    int* urow;             // [batch][nb][4]: finished inverse tiles U(j, j+1 ..) per row slice (fused inverse only)
+    int fused;             // 1: the triangular inverse U = L^-T (strictly upper blocks) is computed by the same kernel
     int ntasks;
     int compact_diag;      // 1: small-code diagonal-block panels (factor buffers larger than L2), see chol128.cuh
     long long timeout;     // cycles
@@ -98,6 +100,10 @@ __device__ __noinline__ void pll_diag_block(double* dsm, double* blk, int np, do
     if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag), "r"(1) : "memory");   // the solves of column j may start
     c128::store_L_part<false>(dsm, blk, np);
     c128::store_DU(dsm, du);
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag), "r"(2) : "memory");   // DU is there too
     const double* pivs = dsm + c128::OFF_PIV;
     if (tid == 0) {
         for (int c = 0; c < NB; ++c)
@@ -128,6 +134,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
     const unsigned full0 = sm_u + PLL_DATA_BYTES, empty0 = full0 + 8 * STAGES, dlbar0 = empty0 + 8 * STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = P.v.nb, np = P.v.np;
+    const CUtensorMap* const mapA = (MT == NB) ? &maps.km[SRC_F] : (MT == NB / 2 ? &maps.km64 : &maps.km32);      // F, MT-row boxes
+    const CUtensorMap* const mapDU = (MT == NB) ? &maps.km[SRC_DU] : (MT == NB / 2 ? &maps.du64 : &maps.du32);     // DU, MT-row boxes
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -137,7 +145,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
 #pragma unroll
         for (int s = 0; s < 4; ++s) mbar_init(dlbar0 + 8 * s, 1);
         mbar_fence_init();
-        tma_prefetch_desc(MT == NB ? &maps.km[SRC_F] : (MT == NB / 2 ? &maps.km64 : &maps.km32));
+        tma_prefetch_desc(mapA);
         tma_prefetch_desc(&maps.km[SRC_F]);
         tma_prefetch_desc(&maps.km[SRC_DL]);
     }
@@ -154,66 +162,97 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         const int ticket = s_ticket;
         if (ticket >= P.ntasks) break;
         fence_proxy_async();                         // generic accesses of the previous task -> before this task's TMA writes
-        // ---- decode: ticket = ((colbase(j) + (i - j)) * H + h) * batch + b,  colbase(j) = j nb - j (j-1) / 2
+        // ---- decode.  ticket = (slot * H + h) * batch + b; `slot` enumerates tiles.
+        //   Cholesky only : column-major lower triangle, slot = colbase(j) + (i - j), colbase(j) = j nb - j (j-1) / 2
+        //   fused inverse : column 0: nb Cholesky tiles; column c >= 1: the nb - c Cholesky tiles (i, c), i >= c, followed by
+        //                   the c - 1 inverse tiles U(jt, c - 1), jt < c - 1 (one column late: the tiles of the next
+        //                   Cholesky column, which are on the dependency chain, are never queued behind them for long);
+        //                   at the very end the nb - 1 inverse tiles of the last block column.  nb^2 slots.
         const int b = ticket % P.batch;
         const int x = ticket / P.batch;
         const int h = x % H;
         const int y = x / H;
-        int j = (int)(((double)(2 * nb + 1) - sqrt((double)(2 * nb + 1) * (double)(2 * nb + 1) - 8.0 * (double)y)) * 0.5);
-        j = max(0, min(j, nb - 1));
-        while (j > 0 && j * nb - j * (j - 1) / 2 > y) --j;
-        while (j + 1 < nb && (j + 1) * nb - (j + 1) * j / 2 <= y) ++j;
-        const int i = j + (y - (j * nb - j * (j - 1) / 2));
+        int kind = 0, i, j;                          // kind 0: Cholesky tile (i, j); kind 1: inverse tile U(j, i), j < i
+        if (!P.fused) {
+            j = (int)(((double)(2 * nb + 1) - sqrt((double)(2 * nb + 1) * (double)(2 * nb + 1) - 8.0 * (double)y)) * 0.5);
+            j = max(0, min(j, nb - 1));
+            while (j > 0 && j * nb - j * (j - 1) / 2 > y) --j;
+            while (j + 1 < nb && (j + 1) * nb - (j + 1) * j / 2 <= y) ++j;
+            i = j + (y - (j * nb - j * (j - 1) / 2));
+        } else if (y < nb) {
+            j = 0; i = y;
+        } else {
+            const int c = 1 + (y - nb) / (nb - 1), r = (y - nb) % (nb - 1);
+            if (c < nb && r < nb - c) { j = c; i = c + r; }
+            else { kind = 1; i = c - 1; j = (c < nb) ? r - (nb - c) : r; }
+        }
         const int moff = h * MT;
         double* Fb = P.v.F + (size_t)b * P.v.fstride;
-        double* Ct = Fb + ((size_t)i * NB + moff) * np + (size_t)j * NB;       // this task's rows of tile (i, j)
-        const int* rd_i = P.rowdone + ((size_t)b * nb + i) * 4 + h;
-        const int* rd_j = P.rowdone + ((size_t)b * nb + j) * 4;
+        // operands: acc += A_k B_k^T over K blocks [k0, k1)
+        //   Cholesky : A_k = L(i, k) rows of this slice, B_k = L(j, k); k in [0, j); solve with DL_j; result -> tile (i, j)
+        //   inverse  : A_k = U(j, k) rows of this slice (U(j, j) = DU_j), B_k = L(i, k); k in [j, i); solve with DL_i,
+        //              negated (U(j,i) = -[sum_k U(j,k) L(i,k)^T] inv(L_ii)) -> tile (j, i) in the upper triangle
+        const int arow = kind ? j : i, brow = kind ? i : j;
+        const int k0 = kind ? j : 0, k1 = kind ? i : j;
+        const int dlb = kind ? i : j;
+        double* Ct = Fb + ((size_t)arow * NB + moff) * np + (size_t)(kind ? i : j) * NB;       // this task's rows of its output tile
+        const int* fl_a = (kind ? P.urow : P.rowdone) + ((size_t)b * nb + arow) * 4 + h;     // progress of operand A's row slice
+        const int* fl_b = P.rowdone + ((size_t)b * nb + brow) * 4;                            // ... of operand B's block row
 
-        // ---- acc = -A(i,j): the tile loads overlap the pipeline fill
+        // ---- acc = -A(i,j) (Cholesky; the tile loads overlap the pipeline fill) or 0 (inverse)
         double acc[MI][4][2];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
             const int rl = wc.wm * (MT / 2) + mi * 8 + wc.pg;
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
-                const double2 c = *reinterpret_cast<const double2*>(Ct + (size_t)rl * np + wc.wn * 32 + ni * 8 + 2 * wc.t);
+                double2 c = make_double2(0.0, 0.0);
+                if (!kind) c = *reinterpret_cast<const double2*>(Ct + (size_t)rl * np + wc.wn * 32 + ni * 8 + 2 * wc.t);
                 acc[mi][ni][0] = -c.x;
                 acc[mi][ni][1] = -c.y;
             }
         }
 
-        // ---- K loop over blocks k < j
-        const int niter = j * KSTEPS;
-        int seen_i = 0, seen_j = 0;                  // flags observed by this lane (they only grow)
-        // position helpers: iteration `it` of this task lives in ring position (cslot0 + it)
-        const int cslot0 = cslot, cuse0 = cuse;
+        // ---- K loop
+        const int niter = (k1 - k0) * KSTEPS;
+        int ready_a = 0, ready_b = 0;                // K blocks k < ready_* are known to be complete (flags only grow)
+        const int cslot0 = cslot, cuse0 = cuse;      // iteration `it` of this task lives in ring position cslot0 + it
         auto fill = [&](int nxt) {
             if (lane == 0) {
                 const int pos = cslot0 + nxt;
                 const int slot = pos % STAGES, use = cuse0 + pos / STAGES;
                 mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);
-                const int k = nxt / KSTEPS, ks = nxt % KSTEPS;
-                if (ks == 0 || seen_i <= k || seen_j <= k) {
-                    if (seen_i <= k) seen_i = wait_flag_ge(rd_i, k + 1, P, b, 1000 + j);
-                    if (seen_j <= k) {
-                        int v = wait_flag_ge(rd_j, k + 1, P, b, 2000 + j);
+                const int k = k0 + nxt / KSTEPS, ks = nxt % KSTEPS;
+                const bool a_is_du = kind && k == arow;
+                if (ks == 0 || ready_a <= k || ready_b <= k) {
+                    if (a_is_du) {
+                        if (ready_a <= k) { wait_flag_ge(&P.diagdone[(size_t)b * nb + arow], 2, P, b, 5000 + arow); ready_a = k + 1; }
+                    } else if (ready_a <= k) {
+                        // Cholesky: rowdone = finished tiles of the row slice = K blocks; inverse: urow = finished U tiles to
+                        // the right of the diagonal block: U(j, j+1 .. j+v) -> K blocks k <= j + v
+                        const int need = kind ? k - arow : k + 1;
+                        const int v = wait_flag_ge(fl_a, need, P, b, 1000 + k);
+                        ready_a = kind ? arow + v + 1 : v;
+                    }
+                    if (ready_b <= k) {
+                        int v = wait_flag_ge(fl_b, k + 1, P, b, 2000 + k);
 #pragma unroll
-                        for (int hh = 1; hh < H; ++hh) v = min(v, wait_flag_ge(rd_j + hh, k + 1, P, b, 3000 + j));
-                        seen_j = v;
+                        for (int hh = 1; hh < H; ++hh) v = min(v, wait_flag_ge(fl_b + hh, k + 1, P, b, 3000 + k));
+                        ready_b = v;
                     }
                     fence_proxy_async();
                 }
                 const unsigned fb = full0 + 8 * slot;
                 mbar_arrive_expect_tx(fb, STAGE_BYTES);
                 const unsigned dA = sm_u + slot * STAGE_BYTES, dB = dA + ABYTES;
-                const CUtensorMap* ma = (MT == NB) ? &maps.km[SRC_F] : (MT == NB / 2 ? &maps.km64 : &maps.km32);
+#pragma unroll
+                for (int hh = 0; hh < BK / TMA_BOX_K; ++hh) {
+                    if (a_is_du) tma_load_3d(dA + hh * (MT * 128), mapDU, ks * BK + hh * TMA_BOX_K, arow * NB + moff, b, fb);
+                    else tma_load_3d(dA + hh * (MT * 128), mapA, k * NB + ks * BK + hh * TMA_BOX_K, arow * NB + moff, b, fb);
+                }
 #pragma unroll
                 for (int hh = 0; hh < BK / TMA_BOX_K; ++hh)
-                    tma_load_3d(dA + hh * (MT * 128), ma, k * NB + ks * BK + hh * TMA_BOX_K, i * NB + moff, b, fb);
-#pragma unroll
-                for (int hh = 0; hh < BK / TMA_BOX_K; ++hh)
-                    tma_load_3d(dB + hh * (NB * 128), &maps.km[SRC_F], k * NB + ks * BK + hh * TMA_BOX_K, j * NB, b, fb);
+                    tma_load_3d(dB + hh * (NB * 128), &maps.km[SRC_F], k * NB + ks * BK + hh * TMA_BOX_K, brow * NB, b, fb);
             }
             __syncwarp();
         };
@@ -233,7 +272,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         }
         __syncthreads();                             // every warp is done with the ring: shared memory is free
 
-        if (i == j) {
+        if (!kind && i == j) {
             // ---- diagonal tile: store C = A - sum; the CTA that completes the tile factors it
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi) {
@@ -252,7 +291,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 double* dsm = reinterpret_cast<double*>(sm);
                 double* blk = Fb + (size_t)j * NB * np + (size_t)j * NB;
                 // this CTA's rows of the updated block go to shared memory straight from the accumulators; the other
-                // half (64-row tasks) comes back from L2
+                // slices (64- / 32-row tasks) come back from L2
 #pragma unroll
                 for (int mi = 0; mi < MI; ++mi) {
                     const int rl = wc.wm * (MT / 2) + mi * 8 + wc.pg;
@@ -266,8 +305,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                                P.compact_diag != 0);
             }
         } else {
-            // ---- off-diagonal tile: P = C inv(L_jj)^T.  C goes to shared memory in the layout of a K-major operand-A
-            //      stage (4 K chunks of [2 boxes][MT rows][128 B], 16-byte chunk index ^= row % 8)
+            // ---- solve step: out = (-acc) inv(L_dd)^T, d = dlb.  -acc goes to shared memory in the layout of a K-major
+            //      operand-A stage (4 K chunks of [2 boxes][MT rows][128 B], 16-byte chunk index ^= row % 8)
             {
                 const int ks = wc.wn;                // this lane's 8 columns wn*32 + ni*8 + 2t lie in K chunk wn
 #pragma unroll
@@ -284,22 +323,22 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 }
             }
             const unsigned dl_base = sm_u + KSTEPS * ABYTES;
-            auto load_dl = [&](int ks) {             // thread 0: K chunk ks of DL_jj (128 n-rows x 32 k) into its slot
+            auto load_dl = [&](int ks) {             // thread 0: K chunk ks of DL_d (128 n-rows x 32 k) into its slot
                 const int slot = ks % NDL;
                 const unsigned bar = dlbar0 + 8 * slot;
                 mbar_arrive_expect_tx(bar, TMA_B_BYTES);
 #pragma unroll
                 for (int hh = 0; hh < BK / TMA_BOX_K; ++hh)
                     tma_load_3d(dl_base + slot * TMA_B_BYTES + hh * (NB * 128), &maps.km[SRC_DL], ks * BK + hh * TMA_BOX_K,
-                                j * NB, b, bar);
+                                dlb * NB, b, bar);
             };
             if (tid == 0) {
-                wait_flag_ge(&P.diagdone[(size_t)b * nb + j], 1, P, b, 4000 + j);
+                wait_flag_ge(&P.diagdone[(size_t)b * nb + dlb], 1, P, b, 4000 + dlb);
                 fence_proxy_async();
 #pragma unroll
                 for (int ks = 0; ks < NDL; ++ks) load_dl(ks);
             }
-            __syncthreads();                         // C is in shared memory
+            __syncthreads();                         // -acc is in shared memory
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
                 const int slot = ks % NDL;
@@ -322,7 +361,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
             __threadfence();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) st_release_gpu(const_cast<int*>(rd_i), j + 1);
+            // progress of this row slice: Cholesky tile (i, j) -> j + 1 finished tiles; inverse tile U(j, i) -> i - j
+            if (tid == 0) st_release_gpu(const_cast<int*>(fl_a), kind ? i - j : j + 1);
         }
     }
 }
@@ -334,13 +374,23 @@ static int env_i(const char* name, int dflt) {
 }
 // LCGP_PLL_HALF / LCGP_PLL_QUARTER: 64-row / 32-row tasks when nb * batch is at most this (few tiles: the latency of the
 // tiles on the dependency chain matters more than operand reuse)
-static int pll_half_limit() { static const int v = env_i("LCGP_PLL_HALF", 160); return v; }
-static int pll_quarter_limit() { static const int v = env_i("LCGP_PLL_QUARTER", 64); return v; }
+// Defaults: factorisation alone (a pure dependency chain for small batches): 64-row tasks up to 160, 32-row tasks up to 64
+// for nb <= 16.  With the fused inverse the launch is work bound much earlier (its tiles fill the idle SMs), and the
+// wider tiles' better operand reuse wins: 64-row tasks up to 96, no 32-row tasks (measured: config 5 one emulator
+// 0.998 ms with 64-row tasks vs 1.07 (32) / 1.15 (128); config 3 4.29 ms with 128-row tasks vs 4.56 (64) / 5.35 (32)).
+static int pll_half_limit(bool fused) {
+    static const int v = env_i("LCGP_PLL_HALF", -1);
+    return v >= 0 ? v : (fused ? 96 : 160);
+}
+static int pll_quarter_limit(bool fused) {
+    static const int v = env_i("LCGP_PLL_QUARTER", -1);
+    return v >= 0 ? v : (fused ? 0 : 64);
+}
 
-size_t potrf_pll_sync_ints(int nb, int batch) { return 8 + (size_t)6 * batch * nb; }
+size_t potrf_pll_sync_ints(int nb, int batch) { return 8 + (size_t)10 * batch * nb; }
 
 cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, double* logdet_part, int* info,
-                      int* sync, cudaStream_t stream) {
+                      int* sync, cudaStream_t stream, bool fused_inverse) {
     static int sms[MAX_DEVICES];
     static std::atomic<bool> configured[MAX_DEVICES];
     int dev = 0;
@@ -374,8 +424,9 @@ cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, 
     if (e != cudaSuccess) return e;
     // quarter tiles only for small matrices (measured: 1024 x 1 500 -> 450 us, 1024 x 8 533 -> 508, 2048 x 1 1016 -> 914; but
     // 8064 x 1 7.0 -> 8.4 ms: with many block columns the bulk efficiency of the wider tiles wins)
-    const bool quarter = v.nb <= 16 && v.nb * batch <= pll_quarter_limit();
-    const bool half = !quarter && v.nb * batch <= pll_half_limit();
+    const bool fused = fused_inverse && v.nb > 1;
+    const bool quarter = v.nb <= 16 && v.nb * batch <= pll_quarter_limit(fused);
+    const bool half = !quarter && v.nb * batch <= pll_half_limit(fused);
     const int H = quarter ? 4 : (half ? 2 : 1);
     PllParams P;
     P.v = v; P.DLw = DLw; P.DUw = DUw; P.batch = batch; P.logdet_part = logdet_part; P.info = info;
@@ -383,7 +434,9 @@ cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, 
     P.rowdone = sync + 8;
     P.diagdone = P.rowdone + (size_t)4 * batch * v.nb;
     P.diagcnt = P.diagdone + (size_t)batch * v.nb;
-    P.ntasks = v.nb * (v.nb + 1) / 2 * H * batch;
+    P.urow = P.diagcnt + (size_t)batch * v.nb;
+    P.fused = fused ? 1 : 0;
+    P.ntasks = (P.fused ? v.nb * v.nb : v.nb * (v.nb + 1) / 2) * H * batch;
     P.timeout = (long long)env_i("LCGP_PLL_TIMEOUT_MS", 4000) * 2000000LL;   // ~2 GHz
     {   // LCGP_PLL_COMPACT: 0 / 1 force; default: compact code once the factor buffers exceed ~half of the 126 MB L2
         const int f = env_i("LCGP_PLL_COMPACT", -1);

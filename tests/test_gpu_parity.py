@@ -55,7 +55,14 @@ def test_matern32_argument_checks():                    # test_cov.py:18-23, cov
 
 # ---------------------------------------------------------------- stages through the C-ABI
 def _potrf(L, F, npad, q, DL, DU, ldp, info, st, persistent=True):
-    """lcgp_potrf_batched with (persistent left-looking kernel) or without (launch chain) the flag scratch."""
+    """lcgp_potrf_batched with (persistent left-looking kernel) or without (launch chain) the flag scratch;
+    persistent='fused': lcgp_potrf_trtri_batched (factor and triangular inverse in one launch)."""
+    if persistent == 'fused':
+        sb = int(L.lcgp_potrf_scratch_bytes(npad, q))
+        scr = torch.full((sb // 4,), 0x7f7f7f7f, dtype=torch.int32, device=F.device)
+        rc = L.lcgp_potrf_trtri_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), ldp, info.data_ptr(), scr.data_ptr(), sb, st)
+        torch.cuda.synchronize()
+        return rc
     if not persistent:
         return L.lcgp_potrf_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), ldp, info.data_ptr(), None, 0, st)
     sb = int(L.lcgp_potrf_scratch_bytes(npad, q))
@@ -65,7 +72,7 @@ def _potrf(L, F, npad, q, DL, DU, ldp, info, st, persistent=True):
     return rc
 
 
-@pytest.mark.parametrize('persistent', [True, False])
+@pytest.mark.parametrize('persistent', [True, False, 'fused'])
 @pytest.mark.parametrize('n,d,q', [(40, 1, 2), (128, 2, 1), (129, 3, 2), (700, 5, 3), (1500, 8, 2), (2100, 4, 9)])
 def test_build_potrf_trtri_stages(n, d, q, persistent):
     L = _cabi.lib()
@@ -94,9 +101,10 @@ def test_build_potrf_trtri_stages(n, d, q, persistent):
     assert info.cpu().tolist() == [0] * q
     assert rel(F.cpu()[:, low], Lref[:, low]) < 1e-12
     assert rel(ldp.sum(1), torch.log(torch.diagonal(Lref, dim1=1, dim2=2)).sum(1)) < 1e-12
-    sb = int(L.lcgp_trtri_scratch_bytes(npad, q))
-    scr = torch.empty(max(sb // 8, 1), dtype=DT, device=dev)
-    assert L.lcgp_trtri_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), scr.data_ptr(), sb, st) == 0
+    if persistent != 'fused':
+        sb = int(L.lcgp_trtri_scratch_bytes(npad, q))
+        scr = torch.empty(max(sb // 8, 1), dtype=DT, device=dev)
+        assert L.lcgp_trtri_batched(F.data_ptr(), npad, q, DL.data_ptr(), DU.data_ptr(), scr.data_ptr(), sb, st) == 0
     Uref = torch.linalg.solve_triangular(Lref, torch.eye(npad, dtype=DT).expand_as(Lref), upper=False).transpose(1, 2)
     Fc = F.cpu()
     for I in range(nb):
