@@ -91,6 +91,9 @@ size_t lcgp_predict_scratch_bytes(int32_t n, int32_t q_loc, int32_t n0);
  *        small emulators on its own streams);
  *        bit8 (LCGP_FLAG_NO_LOOKAHEAD) = do not run the Cholesky panel chain on the library's internal
  *        high-priority stream (default: it overlaps the bulk of the previous trailing update).
+ *        The internal streams are a process-wide pool per device: concurrent callers with the default group count
+ *        serialise on it, so multi-threaded callers should pass 1 in bits 4-7 (lcgp_plan_* does); a call made while
+ *        `stream` is being captured is detected and kept on `stream` alone.
  * After the call the workspace holds L_k, L_k^{-T}, alpha_k (= CinvMs, lcgp.py:781) and m_k (= mks,
  * lcgp.py:779) for lcgp_predict / lcgp_get_aux -- i.e. it also replaces
  * _compute_aux_predictive_quantities_rep (lcgp.py:728-803) and compute_aux_predictive_quantities

@@ -235,8 +235,25 @@ zmat_kernel(int n, int np, int p, int q, const double* __restrict__ YR, const do
     double acc[KC];
 #pragma unroll
     for (int c = 0; c < KC; ++c) acc[c] = 0.0;
-    for (int i = lane; i < n; i += 32) {
-        const double yv = YR[(size_t)j * n + i];
+    // 4 columns per lane and trip: 36 independent loads in flight (one warp per output row: few warps per SM, so the
+    // loop is latency bound; it took 5 % of a config-3 evaluation with one column per trip)
+    const double* yr = YR + (size_t)j * n;
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+        double yv[4], mv[4][KC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) yv[u] = yr[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < KC; ++c) mv[u][c] = (k0 + c < q) ? mk[(size_t)(k0 + c) * np + i + 32 * u] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)                  // same summation order as the one-column loop
+#pragma unroll
+            for (int c = 0; c < KC; ++c) acc[c] += yv[u] * mv[u][c];
+    }
+    for (; i < n; i += 32) {
+        const double yv = yr[i];
 #pragma unroll
         for (int c = 0; c < KC; ++c)
             if (k0 + c < q) acc[c] += yv * mk[(size_t)(k0 + c) * np + i];
@@ -377,6 +394,14 @@ static int nll_grad_impl(const lcgp_problem* P, const double* ell, const double*
     // The persistent Cholesky kernel keeps every SM it gets until its tickets run out, so concurrent groups mostly run
     // one after the other and only overlap at their tails; few, small matrices are better off in ONE launch (all
     // their tiles advance together) unless the caller / environment asked for a group count.
+    {   // under stream capture by the CALLER the library's pooled side streams must not be pulled into the capture
+        // (another thread waiting on them would invalidate it): everything stays on the caller's stream
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+            G = 1;
+            flags |= LCGP_FLAG_NO_LOOKAHEAD;
+        }
+    }
     const bool pll = potrf_use_pll(w.nb, q);        // decided on this call's whole batch, not per stream group
     if (pll && ((flags >> 4) & 15) == 0 && !std::getenv("LCGP_STREAMS") && (q < 8 || w.nb <= 16)) G = 1;
     // Look-ahead uses the library's shared high-priority streams: skipped when the caller asked for "everything on

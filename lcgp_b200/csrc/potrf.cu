@@ -16,7 +16,7 @@
 namespace lcgp {
 
 // ---- staging-engine selection and tensor-map encoding ---------------------------------------------
-bool gemm_use_tma() {
+static bool gemm_tma_requested() {
     static const bool v = [] {
         const char* e = std::getenv("LCGP_GEMM");
         return !(e && std::strcmp(e, "cpasync") == 0);   // default: TMA engine
@@ -84,6 +84,11 @@ int gemm_tma_min_kblocks() {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn();
+// TMA engine unless LCGP_GEMM=cpasync -- or the driver does not export cuTensorMapEncodeTiled, in which case every GEMM
+// (and the Cholesky, through the launch chain) runs on the cp.async engine instead of failing
+bool gemm_use_tma() { return gemm_tma_requested() && encode_fn() != nullptr; }
 
 static EncodeTiledFn encode_fn() {
     static const EncodeTiledFn fn = [] {

@@ -282,7 +282,7 @@ class LCGP:
                  device_preprocess: Optional[bool] = None):
         self.verbose = verbose
         self.robust_mean = robust_mean
-        self.rep_standardize_ybar = rep_standardize_ybar
+        self._rep_standardize_ybar = bool(rep_standardize_ybar)
         self.parameter_clamp_flag = parameter_clamp_flag
         self._device = device
         self._engine_factory = engine_factory
@@ -355,6 +355,23 @@ class LCGP:
         self._ghat_dev = self._gvar_dev = None
         self.psi_c = None
         self.n_evals = 0
+
+    @property
+    def rep_standardize_ybar(self):
+        return self._rep_standardize_ybar
+
+    @rep_standardize_ybar.setter
+    def rep_standardize_ybar(self, flag):
+        """The reference marks this flag "can toggle" (lcgp.py:49); the engine's constant data (ybar or ybar_s, t) depend
+        on it, so a change drops the engine and the cached predictive quantities -- objective, factor and the output maps
+        of predict_rep then all use the same standardisation.  phi / diag_D stay those of construction, as in the
+        reference."""
+        flag = bool(flag)
+        if flag != self._rep_standardize_ybar:
+            self._rep_standardize_ybar = flag
+            self._engine = None
+            if isinstance(getattr(self, 'q', None), int) and hasattr(self, 'CinvMs'):
+                self._invalidate_aux()
 
     # ------------------------------------------------------------------ display
     def __repr__(self):

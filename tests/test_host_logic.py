@@ -290,3 +290,24 @@ def test_lbfgsb_machine_equals_scipy_minimize():
         assert (r.nfev, r.nit, bool(r.success)) == (m.nfev, m.nit, m.success)
         assert np.array_equal(r.x, m.x) and r.fun == float(m.f)
     assert not m.advance()                              # stays stopped
+
+
+def test_toggling_rep_standardize_ybar_rebuilds_the_engine():
+    """The reference marks rep_standardize_ybar "can toggle" (lcgp.py:49).  The engine's constant data depend on it, so a
+    toggle must drop the engine and the cached predictive quantities: the objective afterwards is the one of a model
+    evaluated with that flag, never a mix of the two standardisations."""
+    from helpers import OracleEngine, make_ragged_rep_data
+    x, y, _ = make_ragged_rep_data(seed=4, n_unique=30, p=3, d=2)
+    m = LCGP(y=y, x=x, q=2, submethod='rep', engine_factory=OracleEngine)
+    f_std = float(m.loss())
+    eng = m.engine
+    m.rep_standardize_ybar = False
+    assert m._engine is None and bool(torch.isnan(m.CinvMs).all())
+    f_raw = float(m.loss())
+    assert m.engine is not eng and abs(f_raw - f_std) > 1e-6 * abs(f_std)
+    m.rep_standardize_ybar = True
+    assert abs(float(m.loss()) - f_std) <= 1e-13 * abs(f_std)
+    m.rep_standardize_ybar = True                       # no change: the engine stays
+    e2 = m.engine
+    m.rep_standardize_ybar = 1
+    assert m.engine is e2
