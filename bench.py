@@ -143,6 +143,14 @@ def dgemm_peak(device, n=8192, reps=4, sustain_s=4.0):
 def build_model(cfg_name):
     from lcgp_b200 import LCGP, synthetic
     x, y, x0, y0, mk = synthetic.make_config(cfg_name)
+    # lazy one-off initialisation (CUDA context, cuBLAS handle, NCCL communicator) is not construction time
+    dev = torch.device('cuda', torch.cuda.current_device())
+    a = torch.ones(256, 256, dtype=torch.float64, device=dev)
+    (a @ a).sum().item()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(a)
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
     t0 = time.time()
     model = LCGP(y=y, x=x, **mk)
     return model, time.time() - t0, (x, y, mk)

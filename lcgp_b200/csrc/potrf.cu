@@ -40,9 +40,11 @@ constexpr int LCGP_MAX_PANELS = 4096;
 static int half_tile_limit() { static const int v = env_clamped("LCGP_HALF_TILES", 74, 0, 1 << 20); return v; }
 
 // LCGP_POTRF = pll (one persistent kernel per factorisation, potrf_pll.cu) | panels (launch chain below) | auto
-// (default): the persistent kernel except for large batches of large matrices (>= 16 matrices of >= 32 block columns),
-// where the launch chain with its K = 1024 trailing updates is still ~1.5 % faster (config 4 on one GPU: 169.0 vs
-// 171.5 ms; profiles/r2_potrf_pll_vs_panels.txt) -- everywhere else the persistent kernel wins by 10-45 %.
+// (default): the persistent kernel except for large batches of large matrices (>= 8 matrices of >= 32 block columns),
+// where the launch chain with its K = 1024 trailing updates + the merge-based inverse is still 2-4 % faster (config 4,
+// factor + inverse: 334 ms vs 347 ms at 32 latents per GPU, 85 vs 89 ms at 8; equal at 4: every tile of the persistent
+// kernel pays one extra K block for its solve against the dense inverse of the diagonal block) -- everywhere else the
+// persistent kernel wins by 10-45 % (profiles/r2_potrf_*.txt).
 static int potrf_mode() {   // 0 = auto, 1 = pll, 2 = panels
     static const int v = [] {
         const char* e = std::getenv("LCGP_POTRF");
@@ -62,7 +64,7 @@ bool potrf_fuse_trtri() {
 }
 bool potrf_use_pll(int nb, int batch) {
     if (!potrf_use_pll()) return false;
-    return potrf_mode() == 1 || !(batch >= 16 && nb >= 32);
+    return potrf_mode() == 1 || !(batch >= 8 && nb >= 32);
 }
 // LCGP_DIAG = v2 (default: blocked shared-memory kernel, chol128.cuh) | v1 (register-resident column-by-column kernel)
 static bool diag_use_v2() {
