@@ -461,6 +461,10 @@ def run_ours(args):
             'stages': {
                 'build_ms': float(stages[0]), 'cholesky_ms': float(stages[1]), 'trtri_ms': float(stages[2]),
                 'solve_ms': float(stages[3]), 'contract_kernel_ms': float(stages[4]), 'tail_ms': float(stages[5]),
+                # build_A is NOT HBM bound: ncu (profiles/r2_ncu_full_pll_buildA.txt) shows the FP64 ALU pipe active 56 % of the
+                # cycles and DRAM throughput at 14 % (~90 FP64 operations incl. an exp per 8-byte element); the GB/s figure
+                # is kept because north_star asks for it
+                'build_bound': 'fp64 ALU (ncu: sm__pipe_fp64_cycles_active 55.7 %, dram throughput 13.8 %); 1.3 % of the step',
                 'build_gbs': build_bytes / (stages[0] * 1e-3) / 1e9, 'hbm_peak_gbs': peaks['hbm_gbs'],
                 'hbm_peak_source': psrc, 'build_frac_of_hbm': build_bytes / (stages[0] * 1e-3) / 1e9 / peaks['hbm_gbs'],
                 'cholesky_trtri_fused': bool(fused),       # True: cholesky_* below cover factor + inverse (2 n^3 / 3 flop per latent)

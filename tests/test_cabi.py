@@ -54,5 +54,11 @@ def test_sass_has_fp64_tensor_and_async_copy():
         pytest.skip('cuobjdump not available')
     sass = subprocess.run(['cuobjdump', '-sass', _cabi.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass
-    assert sass.count('DMMA.8x8x4') >= 128
-    assert 'LDGSTS' in sass
+    assert sass.count('DMMA.8x8x4') >= 128                # FP64 tensor pipe
+    assert sass.count('UTMALDG') >= 100                    # TMA tensor-tile loads: the DEFAULT staging engine
+    assert 'SYNCS' in sass                                 # mbarriers (TMA completion / full-empty ring)
+    assert 'LDGSTS' in sass                                # cp.async: the fallback engine
+    # the persistent Cholesky kernel itself: DMMA + TMA + global-memory dependency flags in one kernel
+    pll = sass[sass.index('potrf_pll_kernel'):]
+    pll = pll[:pll.index('Function :', 20) if 'Function :' in pll[20:] else len(pll)]
+    assert 'DMMA' in pll and 'UTMALDG' in pll and 'NANOSLEEP' in pll
