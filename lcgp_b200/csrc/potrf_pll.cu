@@ -339,12 +339,23 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 for (int ks = 0; ks < NDL; ++ks) load_dl(ks);
             }
             __syncthreads();                         // -acc is in shared memory
+            // DL is lower triangular: output columns [32 c, 32 c + 32) only need K chunks ks <= c.  The warps are re-mapped
+            // for this step so that the two warps of every SM sub-partition (w and w + 4 share one tensor pipe) take column
+            // chunks c and 3 - c: 5 K chunks per sub-partition instead of 8 (the solve sits on the dependency chain of
+            // every block column, and is one extra K block of every tile).
+            TmaCoord<false, MT> ws = wc;
+            {
+                const int s4 = warp & 3, hi = warp >> 2;
+                ws.wn = hi ? 3 - s4 : s4;
+                ws.wm = s4 >> 1;
+            }
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
                 const int slot = ks % NDL;
                 mbar_wait(dlbar0 + 8 * slot, (dlpar >> slot) & 1);
                 dlpar ^= 1u << slot;
-                tma_compute_stage<false, MT>(sm + ks * ABYTES, sm + KSTEPS * ABYTES + slot * TMA_B_BYTES, acc, wc);
+                if (ks <= ws.wn)
+                    tma_compute_stage<false, MT>(sm + ks * ABYTES, sm + KSTEPS * ABYTES + slot * TMA_B_BYTES, acc, ws);
                 if (NDL < KSTEPS && ks + NDL < KSTEPS) {
                     __syncthreads();                 // every warp has read the slot
                     if (tid == 0) load_dl(ks + NDL);
@@ -352,10 +363,10 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
             }
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi) {
-                const int rl = wc.wm * (MT / 2) + mi * 8 + wc.pg;
+                const int rl = ws.wm * (MT / 2) + mi * 8 + ws.pg;
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
-                    *reinterpret_cast<double2*>(Ct + (size_t)rl * np + wc.wn * 32 + ni * 8 + 2 * wc.t) =
+                    *reinterpret_cast<double2*>(Ct + (size_t)rl * np + ws.wn * 32 + ni * 8 + 2 * ws.t) =
                         make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             }
             __threadfence();
