@@ -372,6 +372,68 @@ def test_fit_emulators_lockstep_equals_sequential_fits():
             assert abs(float(m.loss()) - r['loss']) <= 1e-9 * abs(r['loss'])
 
 
+def test_sharded_evaluation_with_ranks_emulated_on_one_gpu():
+    """The multi-rank path without NCCL (one GPU is enough): W 'ranks' are W engines over the round-robin latent shards
+    of one model, each result packed by lcgp_pack_sharded; the SUM of the packed vectors (what the all-reduce computes)
+    must equal the unsharded evaluation and the oracle; a rank's failed latent shows up in the last slot."""
+    from lcgp_b200.model import CudaEngine
+    x, y, _ = make_ragged_rep_data(seed=14, n_unique=260, p=7, d=3)
+    m, o = _pair(x, y, q=5, submethod='rep', diag_error_structure=[3, 4])
+    move_params(m, o)
+    lLmb, lLmb0, lsig_p, lnug = m.get_param()
+    q, d, p = 5, 3, 7
+    ref = m.engine.evaluate(lLmb, lLmb0, lnug, lsig_p, True)[:1 + p + q * d + 2 * q]
+    data = m._problem_data()
+    for W in (2, 3):
+        total = torch.zeros(1 + p + q * d + 2 * q + 1, dtype=DT, device='cuda')
+        for rank in range(W):
+            idx = torch.arange(q)[rank::W]
+            eng = CudaEngine(phi_loc=m.phi[:, idx], D_loc=m.diag_D[idx], include_host_terms=(rank == 0), **data)
+            eng.evaluate_device(lLmb[idx], lLmb0[idx], lnug[idx], lsig_p, True)
+            loc = torch.full((q,), -1, dtype=torch.int32)
+            loc[idx] = torch.arange(idx.numel(), dtype=torch.int32)
+            flat = torch.full_like(total, float('nan'))
+            eng.pack_sharded(loc.cuda(), q, flat)
+            total += flat
+        assert float(total[-1]) == 0.0
+        assert rel(total[:-1].cpu(), ref) < 1e-13
+    # against the oracle, through the same chain rule the model applies
+    fo, go = o.loss_and_grad()
+    assert abs(float(ref[0]) - fo) <= NLL_TOL * abs(fo)
+    # a NaN parameter on one 'rank' is counted in the last slot
+    bad = lLmb0.clone(); bad[1] = float('nan')
+    idx = torch.arange(q)[1::2]
+    eng = CudaEngine(phi_loc=m.phi[:, idx], D_loc=m.diag_D[idx], include_host_terms=False, **data)
+    eng.evaluate_device(lLmb[idx], bad[idx], lnug[idx], lsig_p, True)
+    loc = torch.full((q,), -1, dtype=torch.int32); loc[idx] = torch.arange(idx.numel(), dtype=torch.int32)
+    flat = torch.zeros(1 + p + q * d + 2 * q + 1, dtype=DT, device='cuda')
+    eng.pack_sharded(loc.cuda(), q, flat)
+    assert float(flat[-1]) == 1.0
+
+
+def test_predict_outputs_kernel_matches_the_formulas():
+    """lcgp_predict_outputs against lcgp.py:915-926 restated in torch: ragged p / n0 / q, with and without scale / shift."""
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(9)
+    for p, q, n0, std in [(7, 3, 5, True), (130, 33, 300, True), (2, 1, 129, False), (64, 64, 1, True)]:
+        Psi = torch.randn(p, q, dtype=DT, generator=g); gh = torch.randn(q, n0, dtype=DT, generator=g)
+        gv = torch.rand(q, n0, dtype=DT, generator=g); nv = torch.rand(p, dtype=DT, generator=g)
+        sc = torch.rand(p, dtype=DT, generator=g) + 0.5 if std else None
+        sh = torch.randn(p, dtype=DT, generator=g) if std else None
+        c = lambda t: None if t is None else t.cuda().contiguous()
+        Pd, ghd, gvd, nvd, scd, shd = map(c, (Psi, gh, gv, nv, sc, sh))
+        outs = [torch.full((p, n0), float('nan'), dtype=DT, device='cuda') for _ in range(3)]
+        ptr = lambda t: None if t is None else t.data_ptr()
+        assert L.lcgp_predict_outputs(Pd.data_ptr(), ghd.data_ptr(), gvd.data_ptr(), nvd.data_ptr(), ptr(scd), ptr(shd), p, q, n0,
+                                      outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), _cabi.stream_ptr()) == 0
+        s1 = torch.ones(p, dtype=DT) if sc is None else sc
+        s0 = torch.zeros(p, dtype=DT) if sh is None else sh
+        mean, conf = Psi @ gh, (Psi ** 2) @ gv
+        assert rel(outs[0].cpu(), mean * s1[:, None] + s0[:, None]) < 1e-13
+        assert rel(outs[2].cpu(), conf * s1[:, None] ** 2) < 1e-13
+        assert rel(outs[1].cpu(), (conf + nv[:, None]) * s1[:, None] ** 2) < 1e-13
+
+
 # ---------------------------------------------------------------- f-1: preprocessing on the device
 @pytest.mark.parametrize('sub,robust', [('rep', True), ('rep', False), ('full', True), ('full', False)])
 def test_device_preprocessing_equals_host_preprocessing(sub, robust):
