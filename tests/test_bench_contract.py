@@ -26,13 +26,13 @@ def test_reference_arm_json_contract():
     j = json.loads(lines[0])
     assert j['impl'] == 'reference' and j['metric'] == 'NLL+grad evals/s' and j['unit'] == 'evals/s'
     assert j['higher_is_better'] is True and j['vs_baseline'] is None and j['dtype'] == 'f64' and j['data'] == 'synthetic'
-    assert j['value'] > 0 and abs(j['ms_per_step'] * j['value'] - 1e3) < 1e-6 * 1e3
+    assert j['value'] > 0 and abs(j['ms_per_eval_extrapolated'] * j['value'] - 1e3) < 1e-6 * 1e3
     assert j['steps'] == 1 and j['n_gpus'] == 1
     cb = j['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == j['value'] and 'latents' in cb['sample']
     assert j['e2e'] == {'value': j['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert j['extrapolated'] is True and j['sampled_latents'] == 1 and j['sample_fraction'] == 1 / 8
-    assert abs(j['sample_ms_per_step'] * 8 - j['ms_per_step']) < 1e-6 * j['ms_per_step']
+    assert abs(j['ms_per_step'] * 8 - j['ms_per_eval_extrapolated']) < 1e-6 * j['ms_per_eval_extrapolated']   # a step = 1 of 8 latents
     cfg = j['config']
     # identical key set and values as the CUDA arm's `config` (bench.workload_desc): no arm-specific text inside
     sys.path.insert(0, ROOT)
