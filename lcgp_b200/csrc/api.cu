@@ -160,7 +160,7 @@ static Workspace layout(int n, int d, int p, int q, int E, void* basep) {
 
 static FactorView view_of(const Workspace& w) {
     FactorView v;
-    v.F = w.F; v.DL = w.DL; v.DU = w.DU; v.np = w.np; v.nb = w.nb; v.fstride = w.fstride; v.dstride = w.dstride;
+    v.F = w.F; v.DL = w.DL; v.DU = w.DU; v.np = w.np; v.nb = w.nb; v.fstride = w.fstride; v.dstride = w.dstride; v.n = w.n;
     return v;
 }
 
@@ -795,7 +795,7 @@ int lcgp_potrf_batched(double* F, int32_t np, int32_t batch, double* DL, double*
     if (np % NB != 0) return LCGP_E_DIM;
     if (scratch && scratch_bytes < lcgp_potrf_scratch_bytes(np, batch)) return LCGP_E_WORKSPACE;
     FactorView v;
-    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB; v.n = np;
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
@@ -818,7 +818,7 @@ int lcgp_potrf_trtri_batched(double* F, int32_t np, int32_t batch, double* DL, d
     if (scratch_bytes < lcgp_potrf_scratch_bytes(np, batch)) return LCGP_E_WORKSPACE;
     if (!potrf_use_pll()) return LCGP_E_ARG;        // the fused form exists for the persistent kernel only
     FactorView v;
-    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB; v.n = np;
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     cudaStream_t st = (cudaStream_t)stream;
     LCGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
@@ -837,7 +837,7 @@ int lcgp_trtri_batched(double* F, int32_t np, int32_t batch, const double* DL, c
     const size_t need = lcgp_trtri_scratch_bytes(np, batch);
     if (need > 0 && (!scratch || scratch_bytes < need)) return LCGP_E_WORKSPACE;
     FactorView v;
-    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB;
+    v.F = F; v.DL = DL; v.DU = DU; v.np = np; v.nb = np / NB; v.n = np;
     v.fstride = (size_t)np * np; v.dstride = (size_t)v.nb * NB * NB;
     return cuda_rc(trtri_batched(v, (double*)scratch, trtri_scratch_blocks(v.nb) * NB * NB, batch, (cudaStream_t)stream));
 }

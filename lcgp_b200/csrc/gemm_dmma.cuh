@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -56,7 +57,14 @@ struct FactorView {
     const double* DU;
     int np, nb;
     size_t fstride, dstride;
+    int n;              // rows / columns that hold data (np when unknown): rows and columns >= n are the identity pad, and the
+                        // kernels skip the MMA steps that would only multiply its structural zeros
 };
+// number of data rows in the last 128-block (1 .. NB)
+__host__ __device__ inline int last_block_rows(const FactorView& v) {
+    const int r = v.n - (v.nb - 1) * NB;
+    return (r < 1 || r > NB) ? NB : r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Accumulator <-> tile coordinates
@@ -93,10 +101,14 @@ struct TmaCoord {
     static constexpr bool kPairs = true;
     static constexpr int kMI = MT / 16;
     int wm, wn, g, t, pg, moff;
+    // Warps w and w + 4 share an SM sub-partition (one tensor pipe).  They take (wm, wn) = (0, s) and (1, 3 - s): every
+    // sub-partition owns one warp of each row half, one of column chunks {0, 1} and one of {2, 3}, and chunks c and
+    // 3 - c -- so that skipping structurally-zero MMA steps by row half, by column half or by triangular column chunk
+    // (tma_compute_stage_skip) always takes the same share of work off every tensor pipe.
     __device__ __forceinline__ TmaCoord() {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         wm = warp >> 2;
-        wn = warp & 3;
+        wn = wm ? 3 - (warp & 3) : (warp & 3);
         g = lane >> 2;
         t = lane & 3;
         pg = perm8(g);
@@ -265,6 +277,64 @@ __device__ __forceinline__ void tma_compute_stage(const unsigned char* __restric
     }
 }
 
+// Structural-zero skipping.  Of the 128-row tile the Job describes, only rows < rows and columns in [col_lo, col_hi)
+// can be nonzero in this K step (a triangular diagonal block, the identity pad of the last block): a warp whose
+// 32 columns lie outside does nothing, one whose row slab starts at slab0 works on its leading 8-row groups only.
+// All conditions are warp uniform.  Masked steps are rare (the first or last K block of a tile, the tiles of the last
+// block row / column), so this variant is COMPACT -- one k-step body in a rolled loop, ~1 KB of code against ~9 KB for
+// the unrolled stage: a second unrolled copy next to the hot loop cost more in instruction fetch (ncu: no-instruction
+// stalls x 5) than the skipped MMAs saved.
+struct StepMask { int rows, col_lo, col_hi; };
+template <bool BNMAJOR, int MT>
+__device__ __forceinline__ void tma_compute_stage_skip(const unsigned char* __restrict__ As, const unsigned char* __restrict__ Bs,
+                                                       double (&acc)[MT / 16][4][2], const TmaCoord<BNMAJOR, MT>& wc,
+                                                       const StepMask& m, int slab0) {
+    constexpr int MI = MT / 16;
+    if (wc.wn * 32 + 32 <= m.col_lo || wc.wn * 32 >= m.col_hi) return;
+    const int groups = (m.rows - slab0 + 7) >> 3;        // leading row groups of this warp's slab that can be nonzero
+    if (groups <= 0) return;
+    const int arow = (wc.wm * (MT / 2) + wc.pg) * 128;
+    const int brow = (wc.wn * 32 + wc.g) * 128;
+    const int cn0 = (wc.g & 1) + ((wc.g & 2) << 2) + ((wc.g & 4) >> 1);
+#pragma unroll 1
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MI], b[4];
+        const int akoff = (kk >> 2) * (MT * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.pg) << 4) + ((wc.t & 1) << 3);
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) a[mi] = *reinterpret_cast<const double*>(As + arow + mi * 1024 + akoff);
+        if (!BNMAJOR) {
+            const int bkoff = (kk >> 2) * (NB * 128) + (((((kk & 3) << 1) | (wc.t >> 1)) ^ wc.g) << 4) + ((wc.t & 1) << 3);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double*>(Bs + brow + ni * 1024 + bkoff);
+        } else {
+            const int k = kk * 4 + wc.t;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = cn0 + 4 * (ni & 1);
+                b[ni] = *reinterpret_cast<const double*>(Bs + (wc.wn * 2 + (ni >> 1)) * (BK * 128) + k * 128 +
+                                                         (((c >> 1) ^ (k & 7)) << 4) + ((c & 1) << 3));
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+            if (mi < groups) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+    }
+}
+
+// A Job opts in with `static constexpr bool kSkips = true`, a member `tail_skip` (K steps at the end of its last K
+// block that hold nothing but padding), `int head_steps(const Params&) const` / `int tail_steps(const Params&) const`
+// (how many K steps at the start / end of the run may have a non-trivial mask; kAllSteps = the whole run) and
+// `StepMask mask(const Params&, int it) const`.
+#ifndef LCGP_SKIP_MODE
+#define LCGP_SKIP_MODE 1   // 0: no structural-zero skipping (A/B builds)
+#endif
+constexpr int kAllSteps = 1 << 24;
+template <class Job, class = void> struct JobSkips { static constexpr bool value = false; };
+template <class Job> struct JobSkips<Job, decltype((void)Job::kSkips)> { static constexpr bool value = Job::kSkips; };
+
 template <class Job, int MT = NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_constant__ GemmMaps maps) {
@@ -290,7 +360,8 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
         mbar_fence_init();
     }
     __syncthreads();
-    const int niter = (job.kb1 - job.kb0) * KSTEPS;
+    int niter = (job.kb1 - job.kb0) * KSTEPS;
+    if constexpr (JobSkips<Job>::value) niter -= job.tail_skip;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // fill iteration `nxt` into ring slot `slot` (`use` = earlier fills of that slot); one lane issues it
@@ -335,15 +406,32 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
 
     int st = 0, nslot = STAGES - 1, nuse = 0;
     unsigned ph = 0;
-    for (int it = 0; it < niter; ++it) {
+    // one K step; MASKED steps go through the structural-zero dispatcher, the others run the plain stage code
+    auto kstep = [&](int it, auto masked_c) {
         const int nxt = it + STAGES - 1;
         if (nxt < niter && warp == (it & 7)) produce(nxt, nslot, nuse);   // the MMA warps take turns as producer
         mbar_wait(full0 + 8 * st, ph);
-        tma_compute_stage<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes, acc, wc);
+        if constexpr (decltype(masked_c)::value)
+            tma_compute_stage_skip<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes,
+                                                      acc, wc, job.mask(p, it), moff + wc.wm * (MT / 2));
+        else
+            tma_compute_stage<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes, acc, wc);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * st);
         if (++st == STAGES) { st = 0; ph ^= 1; }
         if (++nslot == STAGES) { nslot = 0; ++nuse; }
+    };
+    // The masked steps sit at the head and / or the tail of the K run; they get loops of their own so that the body
+    // loop is exactly the plain pipeline (its instruction schedule is what the throughput of the whole kernel hangs on).
+    int it = 0;
+    if constexpr (JobSkips<Job>::value && LCGP_SKIP_MODE != 0) {
+        const int head = min(job.head_steps(p), niter);
+        const int body_end = max(head, niter - job.tail_steps(p));
+        for (; it < head; ++it) kstep(it, std::true_type{});
+        for (; it < body_end; ++it) kstep(it, std::false_type{});
+        for (; it < niter; ++it) kstep(it, std::true_type{});
+    } else {
+        for (; it < niter; ++it) kstep(it, std::false_type{});
     }
     __syncthreads();   // every warp is done with the tiles: the epilogue may reuse shared memory
     job.epilogue(p, acc, reinterpret_cast<double*>(sm), wc);
@@ -414,9 +502,14 @@ __device__ __forceinline__ void store_pair(double* C, size_t ld, const Coord& wc
 //   col >= 0  : left-looking update of block column `col` inside a panel: tiles (I, col), I >= col
 struct SyrkJob {
     static constexpr bool kBNMajor = false;
+    static constexpr bool kSkips = true;     // tiles of the last block row: the pad rows of P_I are zero
+    static constexpr int tail_skip = 0;
     struct Params { FactorView v; int kb0, kb1, jstart, col, jend; };
     int kb0, kb1, I, J;
     double* base;
+    __device__ int head_steps(const Params& p) const { return (I == p.v.nb - 1 && last_block_rows(p.v) <= NB - 8) ? kAllSteps : 0; }
+    __device__ int tail_steps(const Params&) const { return 0; }
+    __device__ StepMask mask(const Params& p, int) const { return StepMask{I == p.v.nb - 1 ? last_block_rows(p.v) : NB, 0, NB}; }
     __device__ bool init(const Params& p) {
         if (p.col >= 0) {
             I = p.col + blockIdx.x;
@@ -467,9 +560,16 @@ struct SyrkJob {
 // ---- Cholesky panel solve:  P_I = A[I][jb] * inv(L_jb,jb)^T  (in place), I > jb --------------
 struct TrsmJob {
     static constexpr bool kBNMajor = false;
+    static constexpr bool kSkips = true;     // inv(L_jb,jb) is lower triangular: output column c needs k <= c; last block row: pad rows
+    static constexpr int tail_skip = 0;
     struct Params { FactorView v; int jb; };
     int kb0, kb1, I;
     double* base;
+    __device__ int head_steps(const Params&) const { return kAllSteps; }
+    __device__ int tail_steps(const Params&) const { return 0; }
+    __device__ StepMask mask(const Params& p, int it) const {
+        return StepMask{I == p.v.nb - 1 ? last_block_rows(p.v) : NB, BK * it, NB};
+    }
     __device__ bool init(const Params& p) {
         I = p.jb + 1 + blockIdx.x;
         if (I >= p.v.nb) return false;
@@ -504,8 +604,15 @@ struct TrtriParams {
 
 struct TrtriG1Job {
     static constexpr bool kBNMajor = false;
+    static constexpr bool kSkips = true;     // first K block: A operand = upper-triangular DU_J; Kp = last block: pad rows of L are zero
+    static constexpr int tail_skip = 0;
     typedef TrtriParams Params;
     int kb0, kb1, J, Kp, a, b, jl, kl;
+    __device__ int head_steps(const Params& p) const { return (Kp == p.v.nb - 1 && last_block_rows(p.v) <= NB - BK) ? kAllSteps : KSTEPS; }
+    __device__ int tail_steps(const Params&) const { return 0; }
+    __device__ StepMask mask(const Params& p, int it) const {
+        return StepMask{it < KSTEPS ? BK * (it + 1) : NB, 0, Kp == p.v.nb - 1 ? last_block_rows(p.v) : NB};
+    }
     __device__ bool init(const Params& p) {
         a = blockIdx.z * 2 * p.s;
         b = a + p.s;
@@ -537,8 +644,16 @@ struct TrtriG1Job {
 
 struct TrtriG2Job {
     static constexpr bool kBNMajor = true;
+    static constexpr bool kSkips = true;     // last K block: B operand = upper-triangular DU_I (column c needs k' <= c); I = last block: pad columns
+    static constexpr int tail_skip = 0;
     typedef TrtriParams Params;
     int kb0, kb1, J, I, a, b, jl;
+    __device__ int head_steps(const Params& p) const { return (I == p.v.nb - 1 && last_block_rows(p.v) <= NB - BK) ? kAllSteps : 0; }
+    __device__ int tail_steps(const Params&) const { return KSTEPS - 1; }
+    __device__ StepMask mask(const Params& p, int it) const {
+        const int itl = it - (kb1 - 1 - kb0) * KSTEPS;       // >= 0 inside the last K block
+        return StepMask{NB, itl > 0 ? BK * itl : 0, I == p.v.nb - 1 ? last_block_rows(p.v) : NB};
+    }
     __device__ bool init(const Params& p) {
         a = blockIdx.z * 2 * p.s;
         b = a + p.s;

@@ -195,6 +195,10 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         const int arow = kind ? j : i, brow = kind ? i : j;
         const int k0 = kind ? j : 0, k1 = kind ? i : j;
         const int dlb = kind ? i : j;
+        // structural zeros (tma_compute_stage_skip): pad rows of the last block row (Cholesky tiles (nb-1, j)), pad columns
+        // of the last block column (inverse tiles U(j, nb-1)), and the triangular DU_j that is the first K block of an
+        // inverse tile
+        auto padlim = [&] { return (i == nb - 1) ? last_block_rows(P.v) : NB; };   // i: row of a Cholesky tile, column of an inverse tile
         double* Ct = Fb + ((size_t)arow * NB + moff) * np + (size_t)(kind ? i : j) * NB;       // this task's rows of its output tile
         const int* fl_a = (kind ? P.urow : P.rowdone) + ((size_t)b * nb + arow) * 4 + h;     // progress of operand A's row slice
         const int* fl_b = P.rowdone + ((size_t)b * nb + brow) * 4;                            // ... of operand B's block row
@@ -261,14 +265,29 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
             for (int s = 0; s < STAGES - 1; ++s)
                 if (s < niter) fill(s);
         }
-        for (int it = 0; it < niter; ++it) {
+        // one K step; MASKED steps go through the structural-zero variant.  They get a loop of their own so that the
+        // body loop is exactly the plain pipeline (see gemm_tma_kernel).
+        auto kstep = [&](int it, auto masked_c) {
             const int nxt = it + STAGES - 1;
             if (nxt < niter && warp == (it & 7)) fill(nxt);
             mbar_wait(full0 + 8 * cslot, cuse & 1);
-            tma_compute_stage<false, MT>(sm + cslot * STAGE_BYTES, sm + cslot * STAGE_BYTES + ABYTES, acc, wc);
+            if constexpr (decltype(masked_c)::value)
+                tma_compute_stage_skip<false, MT>(sm + cslot * STAGE_BYTES, sm + cslot * STAGE_BYTES + ABYTES, acc, wc,
+                                                  StepMask{kind ? (it < KSTEPS ? BK * (it + 1) : NB) : padlim(), 0, kind ? padlim() : NB},
+                                                  moff + wc.wm * (MT / 2));
+            else
+                tma_compute_stage<false, MT>(sm + cslot * STAGE_BYTES, sm + cslot * STAGE_BYTES + ABYTES, acc, wc);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * cslot);
             if (++cslot == STAGES) { cslot = 0; ++cuse; }
+        };
+        {
+            int it = 0;
+            if (LCGP_SKIP_MODE != 0) {
+                const int head = (padlim() <= (kind ? NB - BK : NB - 8)) ? niter : (kind ? min(KSTEPS, niter) : 0);
+                for (; it < head; ++it) kstep(it, std::true_type{});
+            }
+            for (; it < niter; ++it) kstep(it, std::false_type{});
         }
         __syncthreads();                             // every warp is done with the ring: shared memory is free
 
@@ -339,16 +358,11 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 for (int ks = 0; ks < NDL; ++ks) load_dl(ks);
             }
             __syncthreads();                         // -acc is in shared memory
-            // DL is lower triangular: output columns [32 c, 32 c + 32) only need K chunks ks <= c.  The warps are re-mapped
-            // for this step so that the two warps of every SM sub-partition (w and w + 4 share one tensor pipe) take column
-            // chunks c and 3 - c: 5 K chunks per sub-partition instead of 8 (the solve sits on the dependency chain of
-            // every block column, and is one extra K block of every tile).
-            TmaCoord<false, MT> ws = wc;
-            {
-                const int s4 = warp & 3, hi = warp >> 2;
-                ws.wn = hi ? 3 - s4 : s4;
-                ws.wm = s4 >> 1;
-            }
+            // DL is lower triangular: output columns [32 c, 32 c + 32) only need K chunks ks <= c.  The two warps of every SM
+            // sub-partition (w and w + 4 share one tensor pipe) hold column chunks c and 3 - c (TmaCoord): 5 K chunks per
+            // sub-partition instead of 8 (the solve sits on the dependency chain of every block column, and is one extra
+            // K block of every tile).
+            const TmaCoord<false, MT>& ws = wc;
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
                 const int slot = ks % NDL;

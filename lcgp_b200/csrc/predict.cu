@@ -21,14 +21,24 @@ struct PredictParams {
 
 struct PredictJob {
     static constexpr bool kBNMajor = true;
+    // Skipped MMA steps: the last K block of operand B is the upper-triangular DU_Ib (column c needs k <= c); for the last
+    // column block the columns >= n are padding and so are the last K steps (c0s is zero there).
+    static constexpr bool kSkips = true;
     typedef PredictParams Params;
-    int kb0, kb1, Tb, Ib;
+    int kb0, kb1, Tb, Ib, tail_skip;
     __device__ bool init(const Params& p) {
         Tb = blockIdx.x / p.v.nb;
         Ib = blockIdx.x % p.v.nb;
         kb0 = 0;
         kb1 = Ib + 1;
+        tail_skip = Ib == p.v.nb - 1 ? KSTEPS - (last_block_rows(p.v) + BK - 1) / BK : 0;
         return true;
+    }
+    __device__ int head_steps(const Params& p) const { return (Ib == p.v.nb - 1 && last_block_rows(p.v) <= NB - BK) ? kAllSteps : 0; }
+    __device__ int tail_steps(const Params&) const { return KSTEPS - 1 - tail_skip > 0 ? KSTEPS - 1 - tail_skip : 0; }
+    __device__ StepMask mask(const Params& p, int it) const {
+        const int itl = it - Ib * KSTEPS;                    // >= 0 inside the last K block
+        return StepMask{NB, itl > 0 ? BK * itl : 0, Ib == p.v.nb - 1 ? last_block_rows(p.v) : NB};
     }
     __device__ TileRef a_ref(const Params&, int kb) const { return TileRef{SRC_C, Tb * NB, kb * NB}; }
     __device__ TileRef b_ref(const Params&, int kb) const {   // N-major: rows = k, cols = i
