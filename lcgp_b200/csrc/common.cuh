@@ -58,6 +58,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 // 1 / x by hardware seed (MUFU.RCP64H) + two Newton steps: ~1 ulp, no range checks (x normal, > 0)
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;

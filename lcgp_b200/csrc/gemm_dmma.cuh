@@ -328,6 +328,9 @@ __device__ __forceinline__ void tma_compute_stage_skip(const unsigned char* __re
 // block that hold nothing but padding), `int head_steps(const Params&) const` / `int tail_steps(const Params&) const`
 // (how many K steps at the start / end of the run may have a non-trivial mask; kAllSteps = the whole run) and
 // `StepMask mask(const Params&, int it) const`.
+#ifndef LCGP_LATE_FILL
+#define LCGP_LATE_FILL 1   // 0: the producer always waits for the ring slot before its own MMAs (A/B builds)
+#endif
 #ifndef LCGP_SKIP_MODE
 #define LCGP_SKIP_MODE 1   // 0: no structural-zero skipping (A/B builds)
 #endif
@@ -408,8 +411,22 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
     unsigned ph = 0;
     // one K step; MASKED steps go through the structural-zero dispatcher, the others run the plain stage code
     auto kstep = [&](int it, auto masked_c) {
+        // The MMA warps take turns as producer.  The slot to refill is the one of step it - 1: if a slower warp still
+        // reads it, the producer does its own MMAs first and fills afterwards (one stage of prefetch distance is still
+        // several TMA latencies) instead of idling until the slowest warp has caught up.
         const int nxt = it + STAGES - 1;
-        if (nxt < niter && warp == (it & 7)) produce(nxt, nslot, nuse);   // the MMA warps take turns as producer
+        bool late = false;
+        if (nxt < niter && warp == (it & 7)) {
+#if LCGP_LATE_FILL
+            unsigned ok = 0;
+            if (lane == 0) ok = mbar_test(empty0 + 8 * nslot, (nuse & 1) ^ 1);
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (ok) produce(nxt, nslot, nuse);
+            else late = true;
+#else
+            produce(nxt, nslot, nuse);
+#endif
+        }
         mbar_wait(full0 + 8 * st, ph);
         if constexpr (decltype(masked_c)::value)
             tma_compute_stage_skip<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes,
@@ -418,6 +435,7 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
             tma_compute_stage<Job::kBNMajor, MT>(sm + st * Shape::kStageBytes, sm + st * Shape::kStageBytes + Shape::kABytes, acc, wc);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        if (late) produce(nxt, nslot, nuse);
         if (++st == STAGES) { st = 0; ph ^= 1; }
         if (++nslot == STAGES) { nslot = 0; ++nuse; }
     };

@@ -269,7 +269,19 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         // body loop is exactly the plain pipeline (see gemm_tma_kernel).
         auto kstep = [&](int it, auto masked_c) {
             const int nxt = it + STAGES - 1;
-            if (nxt < niter && warp == (it & 7)) fill(nxt);
+            bool late = false;                       // see gemm_tma_kernel: a producer whose slot is still being read fills after its MMAs
+            if (nxt < niter && warp == (it & 7)) {
+#if LCGP_LATE_FILL
+                const int pos = cslot0 + nxt;
+                unsigned ok = 0;
+                if (lane == 0) ok = mbar_test(empty0 + 8 * (pos % STAGES), ((cuse0 + pos / STAGES) & 1) ^ 1);
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) fill(nxt);
+                else late = true;
+#else
+                fill(nxt);
+#endif
+            }
             mbar_wait(full0 + 8 * cslot, cuse & 1);
             if constexpr (decltype(masked_c)::value)
                 tma_compute_stage_skip<false, MT>(sm + cslot * STAGE_BYTES, sm + cslot * STAGE_BYTES + ABYTES, acc, wc,
@@ -279,6 +291,7 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
                 tma_compute_stage<false, MT>(sm + cslot * STAGE_BYTES, sm + cslot * STAGE_BYTES + ABYTES, acc, wc);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * cslot);
+            if (late) fill(nxt);
             if (++cslot == STAGES) { cslot = 0; ++cuse; }
         };
         {
