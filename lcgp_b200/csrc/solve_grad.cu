@@ -115,15 +115,15 @@ cudaError_t solve_alpha(const FactorView& v, const SolveArgs& a, cudaStream_t st
     return cudaGetLastError();
 }
 
-// 1 / x for x >= 1 (here x = 1 + S): hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.
-// Relative error ~1e-16 without the range checks and long dependent chain of the IEEE division; the
-// quotient only weights gradient terms that are summed over n^2 pairs (tolerance 1e-8).
+// 1 / x for x >= 1 (here x = 1 + S): hardware seed r0 (MUFU.RCP64H, relative error e = 1 - x r0 of ~2^-20) and ONE
+// third-order step 1/x = r0 / (1 - e) ~ r0 (1 + e + e^2): error e^3 ~ 2^-60, three FMAs (two Newton steps take four).
+// No range checks, no long dependent chain of the IEEE division; the quotient only weights gradient terms that are
+// summed over n^2 pairs (tolerance 1e-8).
 __device__ __forceinline__ double rcp_ge1(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 
 // ---- fused A^{-1} tile + gradient contraction ---------------------------------------------------
@@ -200,8 +200,10 @@ struct ContractJob {
         int cc[8];                          // this lane's 8 tile columns: (ni, e) -> cc[2 ni + e]
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) { cc[2 * ni] = wc.col(ni, 0); cc[2 * ni + 1] = wc.col(ni, 1); }
-        double acc_s0 = 0.0, acc_nug = 0.0;
-        // pass 1: C0 per element; acc <- G * C0
+        // pass 1: C0 per element; acc <- G * C0.  With sumW = sum G C0 and sumD = sum over the diagonal of G (diagonal
+        // tiles only), the two scalar derivatives are (1 - nu) sumW + nu sumD and sumD - sumW.
+        double sumW = 0.0, sumD = 0.0;
+        const bool dtile = (I == J);
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) {
             const int r = wc.row(mi);
@@ -213,7 +215,7 @@ struct ContractJob {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const double S = fabs(a - xj[m * NB + cc[e]]);
-                    P[e] *= (1.0 + S);
+                    P[e] = fma(P[e], S, P[e]);      // P (1 + S)
                     V[e] -= S;
                 }
             }
@@ -226,15 +228,16 @@ struct ContractJob {
                     const int c = cc[2 * ni + e];
                     const double c0 = P[2 * ni + e] * exp(V[2 * ni + e]);
                     const double G = dsr * srj[c] * acc[mi][ni][e] - al * aj[c];
-                    const double delta = (gi == J * NB + c) ? 1.0 : 0.0;
-                    acc_s0 += G * ((1.0 - nu) * c0 + nu * delta);
-                    acc_nug += G * (delta - c0);
-                    acc[mi][ni][e] = G * c0;
+                    if (dtile && gi == J * NB + c) sumD += G;
+                    const double w = G * c0;
+                    sumW += w;
+                    acc[mi][ni][e] = w;
                 }
         }
         const int warp = tid >> 5, lane = tid & 31;
-        acc_s0 = warp_sum(acc_s0);
-        acc_nug = warp_sum(acc_nug);
+        sumW = warp_sum(sumW);
+        sumD = warp_sum(sumD);
+        const double acc_s0 = (1.0 - nu) * sumW + nu * sumD, acc_nug = sumD - sumW;
         if (lane == 0) { red[0 * 8 + warp] = acc_s0; red[1 * 8 + warp] = acc_nug; }
         // pass 2: sum_ij (G C0)_ij S_m^2 / (1 + S_m) per input dimension m
         for (int m = 0; m < d; ++m) {
