@@ -41,8 +41,8 @@ static int half_tile_limit() { static const int v = env_clamped("LCGP_HALF_TILES
 
 // LCGP_POTRF = pll (one persistent kernel per factorisation, potrf_pll.cu) | panels (launch chain below) | auto
 // (default): the persistent kernel except for large batches of large matrices (>= 8 matrices of >= 32 block columns),
-// where the launch chain with its K = 1024 trailing updates + the merge-based inverse is still 2-4 % faster (config 4,
-// factor + inverse: 334 ms vs 347 ms at 32 latents per GPU, 85 vs 89 ms at 8; equal at 4: every tile of the persistent
+// where the launch chain with its K = 1024 trailing updates + the merge-based inverse is still 1-2 % faster (config 4,
+// factor + inverse: 323 ms vs 330 ms at 32 latents per GPU, 83 vs 84 ms at 8; slower at 4: every tile of the persistent
 // kernel pays one extra K block for its solve against the dense inverse of the diagonal block) -- everywhere else the
 // persistent kernel wins by 10-45 % (profiles/r2_potrf_*.txt).
 static int potrf_mode() {   // 0 = auto, 1 = pll, 2 = panels
