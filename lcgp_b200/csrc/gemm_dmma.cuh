@@ -337,6 +337,10 @@ __device__ __forceinline__ void tma_compute_stage_skip(const unsigned char* __re
 constexpr int kAllSteps = 1 << 24;
 template <class Job, class = void> struct JobSkips { static constexpr bool value = false; };
 template <class Job> struct JobSkips<Job, decltype((void)Job::kSkips)> { static constexpr bool value = Job::kSkips; };
+// A Job with `static constexpr bool kCustomSteps = true` orders its K steps itself: `void step_ref(int it, int& kb, int& ks)`
+// names the K block and the BK-wide step inside it that pipeline iteration `it` loads (default: blocks kb0, kb0 + 1, ...).
+template <class Job, class = void> struct JobSteps { static constexpr bool value = false; };
+template <class Job> struct JobSteps<Job, decltype((void)Job::kCustomSteps)> { static constexpr bool value = Job::kCustomSteps; };
 
 template <class Job, int MT = NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -372,7 +376,8 @@ gemm_tma_kernel(const __grid_constant__ typename Job::Params p, const __grid_con
         if (lane == 0) {
             mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);   // passes at once for the first fill
             mbar_arrive_expect_tx(full0 + 8 * slot, Shape::kStageBytes);
-            const int kb = job.kb0 + nxt / KSTEPS, ks = nxt % KSTEPS;
+            int kb = job.kb0 + nxt / KSTEPS, ks = nxt % KSTEPS;
+            if constexpr (JobSteps<Job>::value) job.step_ref(nxt, kb, ks);
             const TileRef ra = job.a_ref(p, kb), rb = job.b_ref(p, kb);
             const unsigned dA = sm_u + slot * Shape::kStageBytes, dB = dA + Shape::kABytes;
             const CUtensorMap* ma = (MT == NB) ? &maps.km[ra.src] : &maps.km64;   // half tiles read operand A from F only
@@ -622,7 +627,9 @@ struct TrtriParams {
 
 struct TrtriG1Job {
     static constexpr bool kBNMajor = false;
-    static constexpr bool kSkips = true;     // first K block: A operand = upper-triangular DU_J; Kp = last block: pad rows of L are zero
+    // first K block: A operand = upper-triangular DU_J; Kp = last block: pad rows of L are zero.  (Moving the DU block to
+    // the tail of the K run, which pays for the contraction, made this launch 1.3 % slower -- measured, not kept.)
+    static constexpr bool kSkips = true;
     static constexpr int tail_skip = 0;
     typedef TrtriParams Params;
     int kb0, kb1, J, Kp, a, b, jl, kl;

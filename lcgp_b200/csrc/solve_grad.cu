@@ -140,25 +140,38 @@ struct ContractParams {
 
 struct ContractJob {
     static constexpr bool kBNMajor = false;
-    // Skipped MMA steps: the K run ends in the last block, whose columns >= n of U are zero in every data row (tail_skip);
-    // the first K block of operand A is the upper-triangular DU_I (row r is zero left of column r).
+    // Skipped MMA steps: the columns >= n of U in the last block are zero in every data row (tail_skip K steps), and the
+    // diagonal block of operand A is the upper-triangular DU_I (row r is zero left of column r).  The K steps are ORDERED
+    // so that the masked DU steps come LAST (step_ref): first the full blocks I + 1 .. nb - 2, then the valid steps of the
+    // last block, then DU_I.  At the head of the run the row mask took 1.7 % of the tensor-pipe cycles off the kernel
+    // and not a microsecond off its duration (the first steps of a tile run while the pipeline fills); at the tail the
+    // ring is full and the sub-partition's other warp has the pipe to itself.
     static constexpr bool kSkips = true;
+    static constexpr bool kCustomSteps = true;
     typedef ContractParams Params;
-    int kb0, kb1, I, J, tail_skip;
+    int kb0, kb1, I, J, tail_skip, nfull, nlast, ndu;     // K steps of the full blocks, of the last block, of DU_I
     __device__ bool init(const Params& p) {
         if ((int)blockIdx.x >= p.ntiles) return false;
         tri_decode(blockIdx.x, I, J);
         kb0 = I;
         kb1 = p.v.nb;
         tail_skip = KSTEPS - (last_block_rows(p.v) + BK - 1) / BK;
+        const int nblk = kb1 - kb0;
+        nfull = (nblk >= 2 ? nblk - 2 : 0) * KSTEPS;
+        nlast = nblk >= 2 ? KSTEPS - tail_skip : 0;
+        ndu = nblk >= 2 ? KSTEPS : KSTEPS - tail_skip;        // I = nb - 1: DU_I is the last block
         return true;
     }
-    // The row mask of the DU block is NOT used (head_steps = 0): measured, it takes 1.7 % of the tensor-pipe cycles off the
-    // kernel and not a microsecond off its duration -- the first K steps of a tile run while the pipeline fills.
+    __device__ void step_ref(int it, int& kb, int& ks) const {
+        if (it < nfull) { kb = I + 1 + it / KSTEPS; ks = it % KSTEPS; }
+        else if (it < nfull + nlast) { kb = kb1 - 1; ks = it - nfull; }
+        else { kb = I; ks = it - nfull - nlast; }
+    }
     __device__ int head_steps(const Params&) const { return 0; }
-    __device__ int tail_steps(const Params&) const { return 0; }
+    __device__ int tail_steps(const Params&) const { return ndu; }
     __device__ StepMask mask(const Params&, int it) const {   // diagonal tiles: operand B is DU_I as well
-        const int lim = it < KSTEPS ? BK * (it + 1) : NB;
+        const int ks = it - nfull - nlast;
+        const int lim = ks >= 0 ? BK * (ks + 1) : NB;
         return StepMask{lim, 0, I == J ? lim : NB};
     }
     __device__ TileRef a_ref(const Params&, int kb) const {
