@@ -43,6 +43,7 @@ struct PllParams {
     int* urow;             // [batch][nb][4]: finished inverse tiles U(j, j+1 ..) per row slice (fused inverse only)
     int fused;             // 1: the triangular inverse U = L^-T (strictly upper blocks) is computed by the same kernel
     int ntasks;
+    int inv_first;         // fused ticket order inside a block column: diagonal tile, inverse tiles, then the other Cholesky tiles
     int compact_diag;      // 1: small-code diagonal-block panels (factor buffers larger than L2), see chol128.cuh
     long long timeout;     // cycles
 };
@@ -166,7 +167,8 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
         //   Cholesky only : column-major lower triangle, slot = colbase(j) + (i - j), colbase(j) = j nb - j (j-1) / 2
         //   fused inverse : column 0: nb Cholesky tiles; column c >= 1: the nb - c Cholesky tiles (i, c), i >= c, followed by
         //                   the c - 1 inverse tiles U(jt, c - 1), jt < c - 1 (one column late: the tiles of the next
-        //                   Cholesky column, which are on the dependency chain, are never queued behind them for long);
+        //                   Cholesky column, which are on the dependency chain, are never queued behind them for long;
+        //                   P.inv_first puts them between the diagonal tile and the other Cholesky tiles of the column);
         //                   at the very end the nb - 1 inverse tiles of the last block column.  nb^2 slots.
         const int b = ticket % P.batch;
         const int x = ticket / P.batch;
@@ -183,7 +185,13 @@ potrf_pll_kernel(const __grid_constant__ PllParams P, const __grid_constant__ Ge
             j = 0; i = y;
         } else {
             const int c = 1 + (y - nb) / (nb - 1), r = (y - nb) % (nb - 1);
-            if (c < nb && r < nb - c) { j = c; i = c + r; }
+            if (c < nb && P.inv_first) {
+                // diagonal tile first, then the c - 1 inverse tiles (they do not need DL_c: CTAs that would otherwise wait for
+                // the diagonal block have work), then the off-diagonal Cholesky tiles.  Every dependency still has a smaller ticket.
+                if (r == 0) { j = c; i = c; }
+                else if (r < c) { kind = 1; i = c - 1; j = r - 1; }
+                else { j = c; i = r + 1; }
+            } else if (c < nb && r < nb - c) { j = c; i = c + r; }
             else { kind = 1; i = c - 1; j = (c < nb) ? r - (nb - c) : r; }
         }
         const int moff = h * MT;
@@ -476,6 +484,12 @@ cudaError_t potrf_pll(const FactorView& v, double* DLw, double* DUw, int batch, 
     P.fused = fused ? 1 : 0;
     P.ntasks = (P.fused ? v.nb * v.nb : v.nb * (v.nb + 1) / 2) * H * batch;
     P.timeout = (long long)env_i("LCGP_PLL_TIMEOUT_MS", 4000) * 2000000LL;   // ~2 GHz
+    {   // LCGP_PLL_INVFIRST=0: the older order (all Cholesky tiles of a block column, then the inverse tiles).  Measured with
+        // the inverse tiles right behind the diagonal tile: 64 x 1024: 2.25 -> 2.14 ms, config 3 2.33 -> 2.26 ms, config 4 per-GPU
+        // share 41.5 -> 40.8 ms, 8 x 1024 unchanged (with the chain tile (c + 1, c) kept right behind the diagonal tile: 2.17 / 2.29 / 40.9)
+        const int f = env_i("LCGP_PLL_INVFIRST", -1);
+        P.inv_first = f >= 0 ? f : 1;
+    }
     {   // LCGP_PLL_COMPACT: 0 / 1 force; default: compact code once the factor buffers exceed ~half of the 126 MB L2
         const int f = env_i("LCGP_PLL_COMPACT", -1);
         P.compact_diag = f >= 0 ? f : ((size_t)batch * v.fstride * sizeof(double) > ((size_t)64 << 20) ? 1 : 0);
