@@ -40,11 +40,11 @@ constexpr int LCGP_MAX_PANELS = 4096;
 static int half_tile_limit() { static const int v = env_clamped("LCGP_HALF_TILES", 74, 0, 1 << 20); return v; }
 
 // LCGP_POTRF = pll (one persistent kernel per factorisation, potrf_pll.cu) | panels (launch chain below) | auto
-// (default): the persistent kernel except for large batches of large matrices (>= 8 matrices of >= 32 block columns),
-// where the launch chain with its K = 1024 trailing updates + the merge-based inverse is still 1-2 % faster (config 4,
-// factor + inverse: 323 ms vs 330 ms at 32 latents per GPU, 83 vs 84 ms at 8; slower at 4: every tile of the persistent
-// kernel pays one extra K block for its solve against the dense inverse of the diagonal block) -- everywhere else the
-// persistent kernel wins by 10-45 % (profiles/r2_potrf_*.txt).
+// (default): the persistent kernel except for large batches of large matrices (>= 24 matrices of >= 32 block columns),
+// where the launch chain with its K = 1024 trailing updates + the merge-based inverse is still 0.5 % faster (config 4,
+// factor + inverse at the end of round 2: 322.8 ms vs 324.6 ms at 32 latents per GPU; 164.4 vs 162.7 at 16, 83.1 vs 83.2
+// at 8: every tile of the persistent kernel pays one extra K block for its solve against the dense
+// inverse of the diagonal block) -- everywhere else the persistent kernel wins by up to 45 % (profiles/r2_potrf_*.txt).
 static int potrf_mode() {   // 0 = auto, 1 = pll, 2 = panels
     static const int v = [] {
         const char* e = std::getenv("LCGP_POTRF");
@@ -64,7 +64,7 @@ bool potrf_fuse_trtri() {
 }
 bool potrf_use_pll(int nb, int batch) {
     if (!potrf_use_pll()) return false;
-    return potrf_mode() == 1 || !(batch >= 8 && nb >= 32);
+    return potrf_mode() == 1 || !(batch >= 24 && nb >= 32);
 }
 // LCGP_DIAG = v2 (default: blocked shared-memory kernel, chol128.cuh) | v1 (register-resident column-by-column kernel)
 static bool diag_use_v2() {
