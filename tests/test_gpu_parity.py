@@ -182,6 +182,45 @@ def test_full_objective_gradient(n, p, d, q):
     assert abs(float(m.neglpost()) - float(o.neglpost().detach())) <= 1e-9 * abs(float(o.neglpost().detach()))
 
 
+PAD_TAILS = [1, 31, 33, 64, 96, 97, 121, 127]
+
+
+def _check_padded_tail(tail):
+    n = 256 + tail
+    x, y = make_full_data(seed=tail, n=n, p=4, d=3)
+    m, o = _pair(x, y, q=2, submethod='full')
+    move_params(m, o)
+    _check_loss_grad(m, o, o.neglpost_chol)
+    x0 = np.random.default_rng(tail).uniform(0, 1, (70, 3))
+    for a, b in zip(m.predict(x0), o.predict(torch.as_tensor(x0))):
+        assert rel(a, b) <= PRED_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tail', PAD_TAILS)
+def test_every_padded_tail_of_the_last_block(tail):
+    """n = 2 * 128 + tail: the kernels skip the MMA steps that only multiply the identity pad of the last 128-block (K steps
+    beyond n, pad rows of the last block row, pad columns of the last block column, csrc/gemm_dmma.cuh StepMask) -- one
+    case per residue class the masks distinguish (8-row groups, 32-wide K steps / column chunks): objective + gradient +
+    prediction against the oracle (persistent Cholesky + inverse kernel)."""
+    _check_padded_tail(tail)
+
+
+@pytest.mark.gpu
+def test_every_padded_tail_through_the_launch_chain():
+    """The same cases with LCGP_POTRF=panels (SyrkJob / TrsmJob / TrtriG1 / TrtriG2 masks).  The switch is read once per
+    process, hence a subprocess."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ('import sys; sys.path[:0] = [%r, %r]\n'
+            'import test_gpu_parity as T\n'
+            'for t in T.PAD_TAILS: T._check_padded_tail(t)\n'
+            'print("PAD_TAILS_OK")\n') % (root, os.path.join(root, 'tests'))
+    env = dict(os.environ, LCGP_POTRF='panels')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'PAD_TAILS_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_committed_fixtures():
     """Known answers committed under tests/golden (independent of running the oracle on this box)."""
     for case in FIX:
