@@ -206,19 +206,29 @@ def test_every_padded_tail_of_the_last_block(tail):
     _check_padded_tail(tail)
 
 
-@pytest.mark.gpu
-def test_every_padded_tail_through_the_launch_chain():
-    """The same cases with LCGP_POTRF=panels (SyrkJob / TrsmJob / TrtriG1 / TrtriG2 masks).  The switch is read once per
-    process, hence a subprocess."""
+def _padded_tails_in_subprocess(**env_over):
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ('import sys; sys.path[:0] = [%r, %r]\n'
             'import test_gpu_parity as T\n'
             'for t in T.PAD_TAILS: T._check_padded_tail(t)\n'
             'print("PAD_TAILS_OK")\n') % (root, os.path.join(root, 'tests'))
-    env = dict(os.environ, LCGP_POTRF='panels')
-    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, **env_over), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'PAD_TAILS_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_every_padded_tail_through_the_launch_chain():
+    """The same cases with LCGP_POTRF=panels (SyrkJob / TrsmJob / TrtriG1 / TrtriG2 masks).  The switch is read once per
+    process, hence a subprocess."""
+    _padded_tails_in_subprocess(LCGP_POTRF='panels')
+
+
+@pytest.mark.gpu
+def test_fallback_staging_engine_parity():
+    """LCGP_GEMM=cpasync: the cp.async staging engine (taken automatically when the driver does not export
+    cuTensorMapEncodeTiled) runs the same Jobs and epilogues without TMA, masks or the persistent kernel."""
+    _padded_tails_in_subprocess(LCGP_GEMM='cpasync')
 
 
 def test_committed_fixtures():
